@@ -1,0 +1,629 @@
+// chain.cu -- host layer of the four cluster samplers behind the C ABI (include/bsb200.h):
+// argument validation, colouring / ordering / segmentation of the spots, HBM staging, the
+// per-iteration launch schedule (captured once as a CUDA graph), snapshots and error mapping.
+//
+// Replaces the bodies of iterate / iterate_vvv / iterate_t / iterate_t_vvv
+// (/root/reference/src/cluster.cpp:217-710) as seen through their Rcpp glue
+// (src/RcppExports.cpp:14-105).  Output containers follow SURVEY.md App. D.
+#include "chain.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace bsb {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(BSB200_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+KernelsForD *kernel_table() {
+  static KernelsForD table[kMaxD + 1] = {};
+  return table;
+}
+KernelRegistrar::KernelRegistrar(int d, const KernelsForD &k) {
+  KernelsForD &t = kernel_table()[d];
+  if (k.sweep) { t.sweep = k.sweep; t.sweep_smem = k.sweep_smem; t.sweep_max_blocks_per_sm = k.sweep_max_blocks_per_sm; }
+  if (k.loglik) t.loglik = k.loglik;
+  if (k.deconv) { t.deconv = k.deconv; t.deconv_smem = k.deconv_smem; }
+}
+
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(BSB200_ERR_CUDA, "no CUDA device available (%s); libbsb200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= count) return fail(BSB200_ERR_INVALID, "device %d out of range (have %d)", device, count);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(BSB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  return BSB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spot ordering: internal order = (group, colour, original index); segments = runs of at most
+// `seg` spots inside one (group, colour) range; slots numbered in internal order so that every
+// group's partial records are contiguous.
+// ------------------------------------------------------------------------------------------------
+int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups_req, int seg_spots) {
+  ncol = ncolours;
+  ngroups = ngroups_req;
+  perm.resize((size_t) n);
+  inv.resize((size_t) n);
+  std::vector<int64_t> bucket((size_t) ngroups * ncol + 1, 0);
+  auto grp = [&](int64_t j) { return (int) ((j * (int64_t) ngroups) / n); };
+  for (int64_t j = 0; j < n; j++) bucket[(size_t) grp(j) * ncol + colour[j] + 1]++;
+  for (size_t b = 0; b < bucket.size() - 1; b++) bucket[b + 1] += bucket[b];
+  std::vector<int64_t> fill(bucket.begin(), bucket.end() - 1);
+  for (int64_t j = 0; j < n; j++) {
+    const int64_t pos = fill[(size_t) grp(j) * ncol + colour[j]]++;
+    perm[(size_t) pos] = (int32_t) j;
+    inv[(size_t) j] = (int32_t) pos;
+  }
+  seg_begin.clear(); seg_count.clear(); seg_slot.clear();
+  colour_seg_start.assign((size_t) ncol + 1, 0);
+  group_start.assign((size_t) ngroups + 1, 0);
+  // slots in (group, colour) order; launch lists in (colour, group) order
+  std::vector<std::vector<int32_t>> per_colour_begin((size_t) ncol), per_colour_count((size_t) ncol), per_colour_slot((size_t) ncol);
+  int32_t slot = 0;
+  for (int g = 0; g < ngroups; g++) {
+    group_start[(size_t) g] = slot;
+    for (int c = 0; c < ncol; c++) {
+      const int64_t b = bucket[(size_t) g * ncol + c], e = bucket[(size_t) g * ncol + c + 1];
+      for (int64_t s = b; s < e; s += seg_spots) {
+        per_colour_begin[(size_t) c].push_back((int32_t) s);
+        per_colour_count[(size_t) c].push_back((int32_t) std::min<int64_t>(seg_spots, e - s));
+        per_colour_slot[(size_t) c].push_back(slot++);
+      }
+    }
+  }
+  group_start[(size_t) ngroups] = slot;
+  nslots = slot;
+  for (int c = 0; c < ncol; c++) {
+    colour_seg_start[(size_t) c] = (int32_t) seg_begin.size();
+    seg_begin.insert(seg_begin.end(), per_colour_begin[(size_t) c].begin(), per_colour_begin[(size_t) c].end());
+    seg_count.insert(seg_count.end(), per_colour_count[(size_t) c].begin(), per_colour_count[(size_t) c].end());
+    seg_slot.insert(seg_slot.end(), per_colour_slot[(size_t) c].begin(), per_colour_slot[(size_t) c].end());
+  }
+  colour_seg_start[(size_t) ncol] = (int32_t) seg_begin.size();
+  return BSB200_OK;
+}
+
+int choose_groups(int64_t n) { return n >= 262144 ? kGroups : 1; }
+int choose_segment(int64_t n) {
+  int64_t tps = n / ((int64_t) kBlock * 2048);
+  tps = std::max<int64_t>(1, std::min<int64_t>(8, tps));
+  return (int) tps * kBlock;
+}
+
+template <typename T>
+static int upload(DevBuf<T> &buf, const T *host, size_t count, cudaStream_t s) {
+  int rc = buf.alloc(count);
+  if (rc) return rc;
+  if (count) CK(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  return BSB200_OK;
+}
+
+}   // namespace bsb
+
+using namespace bsb;
+
+struct bsb200_chain {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t n = 0, ld = 0;
+  int d = 0, q = 0, nl = 1, maxdeg = 0;
+  bool tdist = false, vvv = false;
+  uint32_t compat = 0, sweep_flags = 0;
+  int nrep = 0, thin = 1;
+  double gamma = 0, alpha = 0, beta = 0;
+  uint64_t seed = 0;
+  SpotOrder ord;
+  ParamLayout PL;
+  StatLayout SL;
+  KernelsForD K{};
+  DevBuf<double> Y, w, params, partials, gsum, stats, T_fixed, mu0c, lambda0, lm0, ybar, plogLik, snap_mu, snap_lambda, snap_w;
+  DevBuf<uint8_t> z;
+  DevBuf<int32_t> ell, orig, seg_begin, seg_count, seg_slot, group_start, snap_z;
+  DevBuf<uint32_t> iter;
+  DevBuf<int> err;
+  std::vector<double> ybar_host;
+  int32_t *h_snap_z = nullptr;   // pinned staging of one snapshot
+  double *h_snap_w = nullptr;
+  cudaGraphExec_t graph_iter = nullptr, graph_batch = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t iters_done = 0;
+  int blocks_per_sm = 1;
+  double setup_ms = 0;
+
+  ~bsb200_chain() {
+    if (graph_iter) cudaGraphExecDestroy(graph_iter);
+    if (graph_batch) cudaGraphExecDestroy(graph_batch);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (h_snap_z) cudaFreeHost(h_snap_z);
+    if (h_snap_w) cudaFreeHost(h_snap_w);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  SweepArgs sweep_args(int colour, uint32_t flags, uint32_t iter_add) const {
+    SweepArgs a{};
+    a.Y = Y.p; a.ld = ld; a.z = z.p; a.w = w.p; a.ell = ell.p; a.maxdeg = maxdeg; a.orig = orig.p;
+    const int s0 = colour < 0 ? 0 : ord.colour_seg_start[(size_t) colour];
+    const int s1 = colour < 0 ? (int) ord.seg_begin.size() : ord.colour_seg_start[(size_t) colour + 1];
+    a.seg_begin = seg_begin.p + s0; a.seg_count = seg_count.p + s0; a.seg_slot = seg_slot.p + s0;
+    a.nseg = s1 - s0;
+    a.params = params.p; a.PL = PL; a.partials = partials.p; a.SL = SL;
+    a.iter = iter.p; a.iter_add = iter_add;
+    a.key0 = (uint32_t) seed; a.key1 = (uint32_t) (seed >> 32);
+    a.gamma = gamma; a.flags = flags | sweep_flags; a.err = err.p;
+    return a;
+  }
+  ParamArgs param_args(bool finalize_only) const {
+    ParamArgs a{};
+    a.PL = PL; a.SL = SL; a.params = params.p; a.partials = partials.p; a.group_start = group_start.p;
+    a.ngroups = ord.ngroups; a.gsum = gsum.p; a.gsum_ready = ord.ngroups > 1; a.stats = stats.p;
+    a.T_fixed = T_fixed.p; a.mu0c = mu0c.p; a.lambda0 = lambda0.p; a.lm0 = lm0.p; a.ybar = ybar.p;
+    a.alpha = alpha; a.beta = beta; a.n = n; a.tdist = tdist; a.vvv = vvv; a.compat = compat;
+    a.key0 = (uint32_t) seed; a.key1 = (uint32_t) (seed >> 32);
+    a.iter = iter.p; a.nrep = nrep; a.thin = thin; a.plogLik = plogLik.p;
+    a.snap_mu = snap_mu.p; a.snap_lambda = snap_lambda.p;
+    a.finalize_only = finalize_only; a.precision_form = 0; a.err = err.p;
+    return a;
+  }
+  void enqueue_reduce_and_param(bool finalize_only, cudaStream_t s) {
+    if (ord.ngroups > 1) launch_reduce_groups(partials.p, group_start.p, ord.ngroups, SL.E, gsum.p, s);
+    launch_param(param_args(finalize_only), s);
+    g_launches++;
+  }
+  void enqueue_sweep(int colour, uint32_t flags, uint32_t iter_add, cudaStream_t s) {
+    SweepArgs a = sweep_args(colour, flags, iter_add);
+    if (a.nseg <= 0) return;
+    K.sweep(tdist, vvv, a, a.nseg, s);
+    g_launches++;
+  }
+  void enqueue_iteration(cudaStream_t s) {
+    enqueue_reduce_and_param(false, s);
+    for (int c = 0; c < ord.ncol; c++) enqueue_sweep(c, 0, 0, s);
+  }
+};
+
+namespace bsb {
+
+static int validate(const bsb200_cluster_args *a) {
+  if (!a) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  if (a->n <= 0 || a->n > 0x7fffff00ll) return fail(BSB200_ERR_INVALID, "n = %lld out of range", (long long) a->n);
+  if (a->d < 1 || a->d > kMaxD) return fail(BSB200_ERR_UNSUPPORTED, "d = %d unsupported (1..%d)", a->d, kMaxD);
+  if (a->q < 2 || a->q > 255) return fail(BSB200_ERR_UNSUPPORTED, "q = %d unsupported (2..255)", a->q);
+  if (a->nrep < 1 || a->thin < 1) return fail(BSB200_ERR_INVALID, "nrep and thin must be positive");
+  if (!a->Y || !a->nbr_ptr || !a->init || !a->mu0 || !a->lambda0) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  if (a->model != BSB200_MODEL_NORMAL && a->model != BSB200_MODEL_T) return fail(BSB200_ERR_INVALID, "unknown model %d", a->model);
+  if (a->precision != BSB200_PRECISION_EQUAL && a->precision != BSB200_PRECISION_VARIABLE) return fail(BSB200_ERR_INVALID, "unknown precision %d", a->precision);
+  for (int64_t j = 0; j < a->n; j++) {
+    if (a->init[j] < 1 || a->init[j] > a->q) return fail(BSB200_ERR_INVALID, "init[%lld] = %d outside 1..q", (long long) j, a->init[j]);
+    const int64_t dg = a->nbr_ptr[j + 1] - a->nbr_ptr[j];
+    if (dg < 0 || dg > kMaxDeg) return fail(BSB200_ERR_UNSUPPORTED, "spot %lld has %lld neighbours (max %d)", (long long) j, (long long) dg, kMaxDeg);
+    for (int64_t e = a->nbr_ptr[j]; e < a->nbr_ptr[j + 1]; e++)
+      if (a->nbr_idx[e] < 0 || a->nbr_idx[e] >= a->n) return fail(BSB200_ERR_INVALID, "neighbour index out of range at spot %lld", (long long) j);
+  }
+  return BSB200_OK;
+}
+
+static int check_device_error(bsb200_chain *ch) {
+  int e = 0;
+  CK(cudaMemcpyAsync(&e, ch->err.p, sizeof(int), cudaMemcpyDeviceToHost, ch->stream));
+  CK(cudaStreamSynchronize(ch->stream));
+  if (e == BSB_DEVERR_NUMERIC)
+    return fail(BSB200_ERR_NUMERIC, "NA in probability vector, empty cluster (Wishart df <= 0) or matrix not positive definite");
+  return BSB200_OK;
+}
+
+static int build_graphs(bsb200_chain *ch) {
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamBeginCapture(ch->stream, cudaStreamCaptureModeThreadLocal));
+  ch->enqueue_iteration(ch->stream);
+  CK(cudaStreamEndCapture(ch->stream, &g));
+  CK(cudaGraphInstantiate(&ch->graph_iter, g, 0));
+  cudaGraphDestroy(g);
+  if (ch->thin > 1 && ch->thin <= 256 && ch->n <= 200000) {   // launch-bound sizes: one graph per thin batch
+    CK(cudaStreamBeginCapture(ch->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < ch->thin; i++) ch->enqueue_iteration(ch->stream);
+    CK(cudaStreamEndCapture(ch->stream, &g));
+    CK(cudaGraphInstantiate(&ch->graph_batch, g, 0));
+    cudaGraphDestroy(g);
+  }
+  return BSB200_OK;
+}
+
+int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
+  const double t0 = now_ms();
+  int rc = validate(a);
+  if (rc) return rc;
+  rc = select_device(a->device);
+  if (rc) return rc;
+  KernelsForD K = kernel_table()[a->d];
+  if (!K.sweep) return fail(BSB200_ERR_UNSUPPORTED, "library was built without kernels for d = %d", a->d);
+
+  std::unique_ptr<bsb200_chain> ch(new bsb200_chain());
+  ch->device = a->device; ch->K = K;
+  ch->n = a->n; ch->d = a->d; ch->q = a->q;
+  ch->tdist = a->model == BSB200_MODEL_T; ch->vvv = a->precision == BSB200_PRECISION_VARIABLE;
+  ch->nl = ch->vvv ? a->q : 1;
+  ch->compat = a->compat; ch->nrep = a->nrep; ch->thin = a->thin;
+  ch->gamma = a->gamma; ch->alpha = a->alpha; ch->beta = a->beta; ch->seed = a->seed;
+  ch->ld = (a->n + 31) / 32 * 32;
+  const int64_t n = a->n;
+  const int d = a->d, q = a->q;
+  if ((a->compat & BSB200_COMPAT_Q3) && ch->vvv && !ch->tdist) ch->sweep_flags |= SW_Q3;
+  if (!ch->tdist && !ch->vvv) ch->sweep_flags |= SW_NO_PAIRS;
+
+  // ---- colouring -------------------------------------------------------------------------------
+  std::vector<int32_t> colour;
+  int32_t ncol = 0;
+  if (a->colour) {
+    if (a->ncolours < 1 || a->ncolours > 64) return fail(BSB200_ERR_INVALID, "ncolours = %d out of range", a->ncolours);
+    colour.assign(a->colour, a->colour + n);
+    ncol = a->ncolours;
+    for (int64_t j = 0; j < n; j++)
+      if (colour[(size_t) j] < 0 || colour[(size_t) j] >= ncol) return fail(BSB200_ERR_INVALID, "colour[%lld] out of range", (long long) j);
+    if (!colouring_is_proper(a->nbr_ptr, a->nbr_idx, n, colour.data())) {
+      colour.clear();   // e.g. hex offsets on a filled rectangle: fall back to greedy
+    }
+  }
+  if (colour.empty()) {
+    rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
+    if (rc) return rc;
+  }
+  ch->ord.build(n, colour.data(), ncol, choose_groups(n), choose_segment(n));
+  const SpotOrder &ord = ch->ord;
+
+  // ---- device staging --------------------------------------------------------------------------
+  CK(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
+  cudaStream_t s = ch->stream;
+  CK(cudaEventCreate(&ch->ev0));
+  CK(cudaEventCreate(&ch->ev1));
+  int maxdeg = 0;
+  for (int64_t j = 0; j < n; j++) maxdeg = std::max<int>(maxdeg, (int) (a->nbr_ptr[j + 1] - a->nbr_ptr[j]));
+  ch->maxdeg = maxdeg;
+  {
+    std::vector<int32_t> ell((size_t) std::max(maxdeg, 1) * ch->ld, -1);
+    std::vector<uint8_t> z0((size_t) ch->ld, 0);
+    for (int64_t i = 0; i < n; i++) {
+      const int64_t j = ord.perm[(size_t) i];
+      z0[(size_t) i] = (uint8_t) (a->init[j] - 1);
+      int e = 0;
+      for (int64_t p = a->nbr_ptr[j]; p < a->nbr_ptr[j + 1]; p++, e++) ell[(size_t) e * ch->ld + i] = ord.inv[(size_t) a->nbr_idx[p]];
+    }
+    if ((rc = upload(ch->ell, ell.data(), ell.size(), s))) return rc;
+    if ((rc = upload(ch->z, z0.data(), z0.size(), s))) return rc;
+    std::vector<int32_t> origp((size_t) ch->ld, 0);
+    std::copy(ord.perm.begin(), ord.perm.end(), origp.begin());
+    if ((rc = upload(ch->orig, origp.data(), origp.size(), s))) return rc;
+    CK(cudaStreamSynchronize(s));   // host vectors go out of scope
+  }
+  if ((rc = upload(ch->seg_begin, ord.seg_begin.data(), ord.seg_begin.size(), s))) return rc;
+  if ((rc = upload(ch->seg_count, ord.seg_count.data(), ord.seg_count.size(), s))) return rc;
+  if ((rc = upload(ch->seg_slot, ord.seg_slot.data(), ord.seg_slot.size(), s))) return rc;
+  if ((rc = upload(ch->group_start, ord.group_start.data(), ord.group_start.size(), s))) return rc;
+  {
+    DevBuf<double> Yraw;
+    if ((rc = upload(Yraw, a->Y, (size_t) n * d, s))) return rc;
+    if ((rc = ch->ybar.alloc((size_t) d))) return rc;
+    if ((rc = ch->Y.alloc((size_t) d * ch->ld))) return rc;
+    CK(cudaMemsetAsync(ch->Y.p, 0, sizeof(double) * d * ch->ld, s));
+    launch_colmeans(Yraw.p, n, d, ch->ybar.p, s);
+    launch_permute_center(Yraw.p, n, n, d, ch->orig.p, ch->ybar.p, ch->Y.p, ch->ld, s);
+    ch->ybar_host.resize((size_t) d);
+    CK(cudaMemcpyAsync(ch->ybar_host.data(), ch->ybar.p, sizeof(double) * d, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  {
+    std::vector<double> w1((size_t) ch->ld, 1.0);
+    if ((rc = upload(ch->w, w1.data(), w1.size(), s))) return rc;
+    std::vector<double> mu0c((size_t) d), lm0((size_t) d, 0.0);
+    for (int c = 0; c < d; c++) mu0c[(size_t) c] = a->mu0[c] - ch->ybar_host[(size_t) c];
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++) lm0[(size_t) i] += a->lambda0[(size_t) j * d + i] * mu0c[(size_t) j];
+    if ((rc = upload(ch->mu0c, mu0c.data(), (size_t) d, s))) return rc;
+    if ((rc = upload(ch->lm0, lm0.data(), (size_t) d, s))) return rc;
+    if ((rc = upload(ch->lambda0, a->lambda0, (size_t) d * d, s))) return rc;
+    ch->PL = make_param_layout(q, d, ch->nl);
+    std::vector<double> p0((size_t) ch->PL.total, 0.0);
+    for (int k = 0; k < q; k++)
+      for (int c = 0; c < d; c++) p0[(size_t) ch->PL.mu + k * d + c] = mu0c[(size_t) c];
+    for (int k = 0; k < ch->nl; k++) std::memcpy(&p0[(size_t) ch->PL.lam + (size_t) k * d * d], a->lambda0, sizeof(double) * d * d);
+    if ((rc = upload(ch->params, p0.data(), p0.size(), s))) return rc;
+    CK(cudaStreamSynchronize(s));
+  }
+  const int nsnap = a->nrep / a->thin + 1;
+  const int nlT = (ch->tdist || ch->vvv) ? ch->nl : 0;
+  const StatLayout SL_run = make_stat_layout(q, d, nlT);
+  const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
+  const size_t Emax = (size_t) std::max(SL_run.E, SL_init.E);
+  if ((rc = ch->partials.alloc((size_t) ord.nslots * Emax))) return rc;
+  if ((rc = ch->gsum.alloc((size_t) ord.ngroups * Emax))) return rc;
+  if ((rc = ch->stats.alloc(Emax))) return rc;
+  if ((rc = ch->T_fixed.alloc((size_t) ch->PL.np))) return rc;
+  if ((rc = ch->plogLik.alloc((size_t) a->nrep))) return rc;
+  if ((rc = ch->snap_mu.alloc((size_t) nsnap * q * d))) return rc;
+  if ((rc = ch->snap_lambda.alloc((size_t) nsnap * ch->nl * d * d))) return rc;
+  if ((rc = ch->snap_z.alloc((size_t) n))) return rc;
+  if ((rc = ch->snap_w.alloc((size_t) n))) return rc;
+  if ((rc = ch->iter.alloc(1))) return rc;
+  if ((rc = ch->err.alloc(1))) return rc;
+  CK(cudaMemsetAsync(ch->iter.p, 0, sizeof(uint32_t), s));
+  CK(cudaMemsetAsync(ch->err.p, 0, sizeof(int), s));
+  CK(cudaMemsetAsync(ch->snap_mu.p, 0, sizeof(double) * nsnap * q * d, s));
+  CK(cudaMemsetAsync(ch->snap_lambda.p, 0, sizeof(double) * nsnap * ch->nl * d * d, s));
+  {
+    std::vector<double> nanv((size_t) a->nrep, std::numeric_limits<double>::quiet_NaN());
+    CK(cudaMemcpyAsync(ch->plogLik.p, nanv.data(), sizeof(double) * a->nrep, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaMallocHost(&ch->h_snap_z, sizeof(int32_t) * n));
+  CK(cudaMallocHost(&ch->h_snap_w, sizeof(double) * n));
+
+  // ---- statistics of the initial state -----------------------------------------------------------
+  if (nlT == 0) {   // normal model, shared precision: sum_j y_j y_j^T never changes -> T_fixed
+    ch->SL = SL_init;
+    const uint32_t keep = ch->sweep_flags;
+    ch->sweep_flags &= ~SW_NO_PAIRS;
+    ch->enqueue_sweep(-1, SW_STATS_ONLY, 0, s);
+    ch->sweep_flags = keep;
+    ch->enqueue_reduce_and_param(true, s);
+    CK(cudaMemcpyAsync(ch->T_fixed.p, ch->stats.p + SL_init.T, sizeof(double) * ch->PL.np, cudaMemcpyDeviceToDevice, s));
+  }
+  ch->SL = SL_run;
+  ch->enqueue_sweep(-1, SW_STATS_ONLY, 0, s);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  param_kernel_init();
+  if ((rc = build_graphs(ch.get()))) return rc;
+  ch->setup_ms = now_ms() - t0;
+  *out = ch.release();
+  return BSB200_OK;
+}
+
+// Runs `iters` iterations.  When `out` is given, snapshots go to its arrays (cluster_impl); the
+// resident-chain interface passes nullptr and snapshots stop at the pinned staging buffers.
+int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double *device_ms, bool honour_cancel) {
+  CK(cudaSetDevice(ch->device));
+  cudaStream_t s = ch->stream;
+  double total_ms = 0.0;
+  int64_t remaining = iters;
+  while (remaining > 0) {
+    const int64_t it0 = ch->iters_done;   // iterations completed; next iteration index = it0 + 1
+    const int64_t next_multiple = ((it0 + 2 + ch->thin - 1) / ch->thin) * ch->thin;
+    const int64_t to_boundary = next_multiple - 1 - it0;   // iterations up to and including the snapshot one
+    const int64_t run = std::min<int64_t>(to_boundary, remaining);
+    CK(cudaEventRecord(ch->ev0, s));
+    if (run == ch->thin && ch->graph_batch) {
+      CK(cudaGraphLaunch(ch->graph_batch, s));
+    } else {
+      for (int64_t i = 0; i < run; i++) CK(cudaGraphLaunch(ch->graph_iter, s));
+    }
+    ch->iters_done += run;
+    remaining -= run;
+    const bool boundary = (ch->iters_done + 1) % ch->thin == 0;
+    if (boundary) {
+      launch_snapshot(ch->z.p, ch->tdist ? ch->w.p : nullptr, ch->orig.p, ch->n, ch->snap_z.p,
+                      ch->tdist ? ch->snap_w.p : nullptr, s);
+      CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n, cudaMemcpyDeviceToHost, s));
+      if (ch->tdist) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaEventRecord(ch->ev1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ch->ev0, ch->ev1));
+    total_ms += ms;
+    if (boundary) {
+      const size_t r = (size_t) ((ch->iters_done + 1) / ch->thin);
+      if (out && r < (size_t) (ch->nrep / ch->thin + 1)) {
+        if (out->z) std::memcpy(out->z + r * ch->n, ch->h_snap_z, sizeof(int32_t) * ch->n);
+        if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n, ch->h_snap_w, sizeof(double) * ch->n);
+        out->rows_done = (int32_t) r + 1;
+      }
+      int rc = check_device_error(ch);
+      if (rc) return rc;
+      if (honour_cancel && g_cancel.load()) {   // early_stop at a thin boundary (src/cluster.cpp:1106)
+        if (device_ms) *device_ms = total_ms;
+        return fail(BSB200_ERR_CANCELLED, "Stopping...");
+      }
+    }
+  }
+  if (device_ms) *device_ms = total_ms;
+  return check_device_error(ch);
+}
+
+// Closes plogLik of the last sweep and copies the device-resident outputs to the host.
+int chain_finish_impl(bsb200_chain *ch, bsb200_cluster_out *out) {
+  cudaStream_t s = ch->stream;
+  ch->enqueue_reduce_and_param(true, s);
+  const int nsnap = ch->nrep / ch->thin + 1, q = ch->q, d = ch->d;
+  if (out->plogLik) CK(cudaMemcpyAsync(out->plogLik, ch->plogLik.p, sizeof(double) * ch->nrep, cudaMemcpyDeviceToHost, s));
+  if (out->mu) CK(cudaMemcpyAsync(out->mu, ch->snap_mu.p, sizeof(double) * nsnap * q * d, cudaMemcpyDeviceToHost, s));
+  if (out->lambda) CK(cudaMemcpyAsync(out->lambda, ch->snap_lambda.p, sizeof(double) * nsnap * ch->nl * d * d, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BSB200_OK;
+}
+
+}   // namespace bsb
+
+extern "C" {
+
+int bsb200_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+
+int64_t bsb200_kernel_launches(void) { return (int64_t) g_launches.load(); }
+
+int bsb200_chain_create(const bsb200_cluster_args *args, bsb200_chain **chain) {
+  if (!chain) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  *chain = nullptr;
+  return chain_create_impl(args, chain);
+}
+
+int bsb200_chain_run(bsb200_chain *chain, int32_t iters, double *device_ms) {
+  if (!chain || iters < 0) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  return chain_run_impl(chain, iters, nullptr, device_ms, false);
+}
+
+int bsb200_chain_profile(bsb200_chain *ch, int32_t iters, double *sweep_ms, int64_t *launches, double *param_ms) {
+  if (!ch || iters < 0) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  CK(cudaSetDevice(ch->device));
+  cudaStream_t s = ch->stream;
+  const int per_iter = ch->ord.ncol + 1;
+  std::vector<cudaEvent_t> ev((size_t) iters * per_iter * 2);
+  for (auto &e : ev) CK(cudaEventCreate(&e));
+  size_t k = 0;
+  for (int i = 0; i < iters; i++) {
+    CK(cudaEventRecord(ev[k++], s));
+    ch->enqueue_reduce_and_param(false, s);
+    CK(cudaEventRecord(ev[k++], s));
+    for (int c = 0; c < ch->ord.ncol; c++) {
+      CK(cudaEventRecord(ev[k++], s));
+      ch->enqueue_sweep(c, 0, 0, s);
+      CK(cudaEventRecord(ev[k++], s));
+    }
+    ch->iters_done++;
+  }
+  CK(cudaStreamSynchronize(s));
+  double sw = 0.0, pm = 0.0;
+  int64_t nl = 0;
+  k = 0;
+  for (int i = 0; i < iters; i++) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+    pm += ms; k += 2;
+    for (int c = 0; c < ch->ord.ncol; c++) {
+      CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      sw += ms; k += 2; nl++;
+    }
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  if (sweep_ms) *sweep_ms = sw;
+  if (param_ms) *param_ms = pm;
+  if (launches) *launches = nl;
+  return check_device_error(ch);
+}
+
+int bsb200_chain_state(bsb200_chain *ch, int32_t *z, double *weights, double *mu, double *lambda,
+                       double *plogLik, int64_t *iters_done) {
+  if (!ch) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  CK(cudaSetDevice(ch->device));
+  cudaStream_t s = ch->stream;
+  const int q = ch->q, d = ch->d;
+  if (z || weights) {
+    launch_snapshot(ch->z.p, ch->w.p, ch->orig.p, ch->n, ch->snap_z.p, ch->snap_w.p, s);
+    if (z) CK(cudaMemcpyAsync(z, ch->snap_z.p, sizeof(int32_t) * ch->n, cudaMemcpyDeviceToHost, s));
+    if (weights) CK(cudaMemcpyAsync(weights, ch->snap_w.p, sizeof(double) * ch->n, cudaMemcpyDeviceToHost, s));
+  }
+  std::vector<double> p((size_t) ch->PL.total);
+  CK(cudaMemcpyAsync(p.data(), ch->params.p, sizeof(double) * p.size(), cudaMemcpyDeviceToHost, s));
+  if (plogLik && ch->iters_done >= 1) {
+    ch->enqueue_reduce_and_param(true, s);   // closes plogLik of the last sweep (idempotent)
+    CK(cudaMemcpyAsync(plogLik, ch->plogLik.p, sizeof(double) * std::min<int64_t>(ch->iters_done + 1, ch->nrep),
+                       cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  if (mu)
+    for (int k = 0; k < q; k++)
+      for (int c = 0; c < d; c++) mu[k * d + c] = p[(size_t) ch->PL.mu + k * d + c] + ch->ybar_host[(size_t) c];
+  if (lambda) std::memcpy(lambda, &p[(size_t) ch->PL.lam], sizeof(double) * ch->nl * d * d);
+  if (iters_done) *iters_done = ch->iters_done;
+  return BSB200_OK;
+}
+
+int bsb200_chain_dry_sweep(bsb200_chain *ch, int32_t *z_new, double *w_new, double *h_prev, double *h_new,
+                           double *prob, int32_t *accepted) {
+  if (!ch) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  CK(cudaSetDevice(ch->device));
+  cudaStream_t s = ch->stream;
+  const size_t n = (size_t) ch->n;
+  DevBuf<int32_t> dz, da;
+  DevBuf<double> dw, dhp, dhn, dpr;
+  int rc;
+  if ((rc = dz.alloc(n)) || (rc = da.alloc(n)) || (rc = dw.alloc(n)) || (rc = dhp.alloc(n)) || (rc = dhn.alloc(n)) || (rc = dpr.alloc(n))) return rc;
+  // parameters of the next iteration are drawn first (k_param advances the iteration counter), the
+  // dry sweep then evaluates that iteration's proposals on the unchanged labels / weights.
+  DevBuf<double> params_keep, plog_keep;
+  if ((rc = params_keep.alloc((size_t) ch->PL.total))) return rc;
+  CK(cudaMemcpyAsync(params_keep.p, ch->params.p, sizeof(double) * ch->PL.total, cudaMemcpyDeviceToDevice, s));
+  ch->enqueue_reduce_and_param(false, s);
+  for (int c = 0; c < ch->ord.ncol; c++) {
+    SweepArgs a = ch->sweep_args(c, SW_DRY, 0);
+    a.dry_znew = dz.p; a.dry_w = dw.p; a.dry_hp = dhp.p; a.dry_hn = dhn.p; a.dry_prob = dpr.p; a.dry_acc = da.p;
+    if (a.nseg > 0) { ch->K.sweep(ch->tdist, ch->vvv, a, a.nseg, s); g_launches++; }
+  }
+  // roll the chain back: parameters and iteration counter as before (the statistics were not touched)
+  CK(cudaMemcpyAsync(ch->params.p, params_keep.p, sizeof(double) * ch->PL.total, cudaMemcpyDeviceToDevice, s));
+  const uint32_t it = (uint32_t) ch->iters_done;
+  CK(cudaMemcpyAsync(ch->iter.p, &it, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  if (z_new) CK(cudaMemcpyAsync(z_new, dz.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  if (accepted) CK(cudaMemcpyAsync(accepted, da.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  if (w_new) CK(cudaMemcpyAsync(w_new, dw.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (h_prev) CK(cudaMemcpyAsync(h_prev, dhp.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (h_new) CK(cudaMemcpyAsync(h_new, dhn.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (prob) CK(cudaMemcpyAsync(prob, dpr.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return check_device_error(ch);
+}
+
+int bsb200_chain_destroy(bsb200_chain *chain) {
+  if (chain) {
+    cudaSetDevice(chain->device);
+    delete chain;
+  }
+  return BSB200_OK;
+}
+
+int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
+  if (!args || !out) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  g_cancel.store(0);
+  bsb200_chain *ch = nullptr;
+  int rc = chain_create_impl(args, &ch);
+  if (rc) return rc;
+  std::unique_ptr<bsb200_chain> guard(ch);
+  const int64_t n = args->n;
+  const int d = args->d, q = args->q, nsnap = args->nrep / args->thin + 1, nl = ch->nl;
+  // row 0 of every output = initial state (src/cluster.cpp:232-237, 462-469); later rows zero until written
+  if (out->z) {
+    std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
+    std::memcpy(out->z, args->init, sizeof(int32_t) * n);
+  }
+  if (out->weights && ch->tdist) {
+    std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
+    for (int64_t j = 0; j < n; j++) out->weights[j] = 1.0;
+  }
+  out->rows_done = 1;
+  out->ncolours = ch->ord.ncol;
+  out->setup_ms = ch->setup_ms;
+  double ms = 0.0;
+  rc = chain_run_impl(ch, args->nrep - 1, out, &ms, true);
+  out->device_ms = ms;
+  if (rc && rc != BSB200_ERR_CANCELLED) return rc;
+  int rc2 = chain_finish_impl(ch, out);
+  if (rc2) return rc2;
+  if (out->mu)
+    for (int k = 0; k < q; k++)
+      for (int c = 0; c < d; c++) out->mu[k * d + c] = args->mu0[c];
+  if (out->lambda)
+    for (int k = 0; k < nl; k++) std::memcpy(out->lambda + (size_t) k * d * d, args->lambda0, sizeof(double) * d * d);
+  if (rc == BSB200_OK) out->rows_done = nsnap;
+  return rc;
+}
+
+}   // extern "C"

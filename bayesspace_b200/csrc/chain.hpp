@@ -1,0 +1,47 @@
+// chain.hpp -- host-side building blocks shared by the cluster and deconvolution samplers.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "common.hpp"
+#include "kernels.hpp"
+#include "util_kernels.hpp"
+
+namespace bsb {
+
+// Owning device buffer.
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t count = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    count = n;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(BSB200_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return BSB200_OK;
+  }
+};
+
+// Internal spot order and the segment / slot / group tables derived from it (chain.cu).
+struct SpotOrder {
+  int ncol = 0, ngroups = 1, nslots = 0;
+  std::vector<int32_t> perm;   // internal position -> original spot
+  std::vector<int32_t> inv;    // original spot -> internal position
+  std::vector<int32_t> seg_begin, seg_count, seg_slot;   // launch lists, colour-major
+  std::vector<int32_t> colour_seg_start;                 // ncol + 1 offsets into the launch lists
+  std::vector<int32_t> group_start;                      // ngroups + 1 offsets into the slots
+  int build(int64_t n, const int32_t *colour, int ncolours, int ngroups, int seg_spots);
+};
+
+int select_device(int device);
+int choose_groups(int64_t n);
+int choose_segment(int64_t n);
+void param_kernel_init();
+
+}   // namespace bsb

@@ -1,0 +1,298 @@
+// deconv_kernels.cu -- k_deconv<D, ADAPT>: one sweep of iterate_deconv (spatialEnhance) for the
+// parents of ONE parent-colour class, instantiated for d = BSB_D.
+//
+// Reference loop replaced: /root/reference/src/cluster.cpp:904-1056
+//   :905-908   jitter draws                    :913-962  per-parent proposal and log-ratio
+//   :969-982   joint accept of the S subspots  :987-995  Robust Adaptive Metropolis update
+//   :998-1008  t-model weights                 :1010-1051 label MH per subspot
+//   :1055-1056 Ychange / plogLik
+// Mapping: one lane per subspot, the S subspots of a parent on S adjacent lanes of one warp, so
+// the zero-sum constraint and the joint accept stay inside a warp (shuffles), the S label updates
+// of a parent run sequentially (r = 0..S-1, live neighbour labels) exactly as in the reference,
+// and parents of one colour class -- never adjacent -- run in parallel.  The same pass
+// accumulates the sufficient statistics of the next iteration, so Y is read and written once.
+#include "deconv.hpp"
+#include "kernels.hpp"
+#include "rng.cuh"
+#include "tile_stats.cuh"
+
+#ifndef BSB_D
+#error "compile with -DBSB_D=<d>"
+#endif
+
+namespace bsb {
+namespace {
+
+struct DeconvSmem {
+  int gL, cL, PL, tile, sws, wvs, acc, red, zs_bytes_off;
+  size_t bytes;
+};
+__host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, int E) {
+  DeconvSmem s;
+  int o = 0;
+  s.gL = o; o += q * D;
+  s.cL = o; o += q;
+  s.PL = o; o += np;
+  o = (o + 1) & ~1;
+  s.tile = o; o += D * kTileLd;
+  s.sws = o; o += kBlock;
+  s.wvs = o; o += kBlock;
+  s.acc = o; o += E;
+  s.red = o; o += 2 * (kBlock / 32);
+  s.zs_bytes_off = o * 8;
+  s.bytes = (size_t) o * 8 + kBlock;
+  return s;
+}
+
+template <int D, bool ADAPT>
+__global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int NP = D * (D + 1) / 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = a.PL.q, E = a.SL.E, S = a.S;
+  const DeconvSmem L = deconv_smem_layout(D, q, NP, E);
+  double *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL, *tile = sm + L.tile, *sws = sm + L.sws;
+  double *wvs = sm + L.wvs, *acc = sm + L.acc, *red = sm + L.red;
+  uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
+  if (*a.err) return;
+  if (!a.stats_only) {
+    const double *P = a.params;
+    for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
+    for (int e = tid; e < q; e += kBlock) s_cL[e] = P[a.PL.cL + e];
+    for (int e = tid; e < NP; e += kBlock) s_PL[e] = P[a.PL.PL + e];
+  }
+  const Key key{a.key0, a.key1};
+  const uint32_t it = *a.iter;
+  const double w_alpha = (double) ((D + 4) / 2);   // quirk Q2 (src/cluster.cpp:809)
+  const double halfD = 0.5 * D;
+  const int gpw = 32 / S;                          // parents per warp
+  const int ppb = (kBlock / 32) * gpw;             // parents per CTA pass
+  const int g = lane / S, r = lane - g * S;
+  const bool lane_valid = g < gpw;
+  const int glane0 = g * S;                        // first lane of this parent's group
+  __syncthreads();
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const int begin = a.seg_begin[seg], count = a.seg_count[seg];
+    for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    double hp_acc = 0.0, nacc_y = 0.0;
+
+    for (int base = 0; base < count; base += ppb) {
+      const int pidx = base + warp * gpw + g;
+      const bool active = lane_valid && pidx < count;
+      const int64_t ip = (int64_t) begin + pidx;
+      const int64_t si = (int64_t) r * a.ld0 + ip;
+      double y[D], e[D];
+      double wj = 1.0;
+      int zk = 0, zfinal = 255;
+      uint32_t j0 = 0, sorig = 0;
+#pragma unroll
+      for (int c = 0; c < D; c++) { y[c] = 0.0; e[c] = 0.0; }
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < D; c++) y[c] = a.Y[((size_t) c * S + r) * a.ld0 + ip];
+        zk = a.z[si];
+        zfinal = zk;
+        if (a.tdist) wj = a.w[si];
+        j0 = (uint32_t) a.orig0[ip];
+        sorig = (uint32_t) r * (uint32_t) a.n0 + j0;
+      }
+      if (!a.stats_only) {   // uniform branch
+        double v[ADAPT ? D : 1];
+#pragma unroll
+        for (int c = 0; c < (ADAPT ? D : 1); c++) v[c] = 0.0;
+        // ---- jitter: rmvnorm(n, 0, I * jitter_scale) (:905-908), transformed by the RAM factor (:922-929)
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < D; c += 2) {
+            double n0v, n1v;
+            rng_normal2(key, P_ERR, sorig, it, (uint32_t) (c >> 1), n0v, n1v);
+            e[c] = a.err_sd * n0v;
+            if (c + 1 < D) e[c + 1] = a.err_sd * n1v;
+          }
+          if (ADAPT) {
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j <= i; j++) s += a.A[((size_t) (i * (i + 1) / 2 + j) * S + r) * a.ld0 + ip] * e[j];
+              v[i] = s;
+            }
+          }
+        }
+        double usq = 0.0;   // |u|^2 of the raw draw, needed by the RAM update
+        if (ADAPT) {
+#pragma unroll
+          for (int c = 0; c < D; c++) { usq += e[c] * e[c]; e[c] = v[c]; }
+        }
+        // ---- zero-sum constraint: subtract the mean over the parent's S subspots (:932-935)
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+          double tot = 0.0;
+          for (int rr = 0; rr < S; rr++) tot += __shfl_sync(0xffffffffu, e[c], glane0 + rr);
+          e[c] -= tot / S;
+        }
+        // ---- log-ratio of the joint proposal (:941-956)
+        double dl = 0.0, quad_old = 0.0, quad_new = 0.0, b_old = 0.0, b_new = 0.0;
+        if (active) {
+          double pen_old = 0.0, pen_new = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; c++) {
+            const double y0 = a.Y0[(size_t) c * a.ld0 + ip];
+            pen_old += (y[c] - y0) * (y[c] - y0);
+            e[c] = y[c] + e[c];   // e now holds the proposed Y
+            pen_new += (e[c] - y0) * (e[c] - y0);
+          }
+          b_old = dotv<D>(y, s_gL + zk * D);
+          b_new = dotv<D>(e, s_gL + zk * D);
+          quad_old = quadform<D>(y, s_PL) - 2.0 * b_old + s_cL[zk];
+          quad_new = quadform<D>(e, s_PL) - 2.0 * b_new + s_cL[zk];
+          dl = -0.5 * wj * (quad_new - quad_old) - a.c * (pen_new - pen_old);
+        }
+        double tot = 0.0;
+        for (int rr = 0; rr < S; rr++) tot += __shfl_sync(0xffffffffu, dl, glane0 + rr);
+        bool accY = false;
+        double dl_z = 0.0, u_acc_z = 0.0, hp_stay = 0.0, hp_move = 0.0;   // inputs of the label scan
+        int zn = 0, nacc_new = 0;
+        if (active) {
+          double probY = exp(tot);
+          if (probY > 1.0) probY = 1.0;
+          if (probY != probY) atomicExch(a.err, BSB_DEVERR_NUMERIC);
+          double u_y, u_unused;
+          rng_uniform2(key, P_SPOT_YACC, j0, it, 0u, u_y, u_unused);
+          accY = sample_two(probY, u_y);   // one draw per parent (:975)
+          if (accY) {
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+              y[c] = e[c];
+              a.Y[((size_t) c * S + r) * a.ld0 + ip] = e[c];
+            }
+            quad_old = quad_new;
+            b_old = b_new;
+            if (r == 0) nacc_y += 1.0;
+          }
+          // ---- Robust Adaptive Metropolis factor update (adaptive_mcmc, :49-65, :987-995)
+          if (ADAPT) {
+            nacc_new = a.nacc[ip] + (accY ? 1 : 0);
+            const bool do_adapt = it > 10u && (a.adapt_before == 0 || it <= (uint32_t) a.adapt_before);
+            if (do_adapt) {
+              const double rate = (double) nacc_new / (double) it;   // cumulative acceptance (quirk Q11)
+              const double step = fmin(1.0, D * pow((double) it, -2.0 / 3));
+              const double kappa = step * (rate - 0.234) / usq;
+              const double sk = sqrt(fabs(kappa));
+              const bool up = kappa >= 0.0;
+              double x[D];
+#pragma unroll
+              for (int c = 0; c < D; c++) x[c] = sk * v[c];
+#pragma unroll
+              for (int k = 0; k < D; k++) {
+                double *Lkk = a.A + ((size_t) (k * (k + 1) / 2 + k) * S + r) * a.ld0 + ip;
+                const double lkk = *Lkk;
+                const double r2 = up ? lkk * lkk + x[k] * x[k] : lkk * lkk - x[k] * x[k];
+                if (!(r2 > 0.0)) atomicExch(a.err, BSB_DEVERR_NUMERIC);
+                const double rr = sqrt(r2), cc = rr / lkk, ss = x[k] / lkk;
+                *Lkk = rr;
+#pragma unroll
+                for (int i = k + 1; i < D; i++) {
+                  double *Lik = a.A + ((size_t) (i * (i + 1) / 2 + k) * S + r) * a.ld0 + ip;
+                  const double lik = up ? (*Lik + ss * x[i]) / cc : (*Lik - ss * x[i]) / cc;
+                  x[i] = cc * x[i] - ss * lik;
+                  *Lik = lik;
+                }
+              }
+            }
+          }
+          // ---- t-model weight (:998-1008)
+          double logw = 0.0;
+          if (a.tdist) {
+            wj = rng_gamma(key, P_SPOT_GAMMA, sorig, it, w_alpha, 2.0 / (quad_old + 4.0));
+            a.w[si] = wj;
+            logw = log(wj);
+          }
+          // ---- label proposal; the density part of the MH ratio is known before the scan (:1011-1027)
+          double u_prop;
+          rng_uniform2(key, P_SPOT_U, sorig, it, 0u, u_prop, u_acc_z);
+          zn = propose_label(zk, q, u_prop);
+          const double lin_p = s_cL[zk] - 2.0 * b_old;
+          const double lin_n = s_cL[zn] - 2.0 * dotv<D>(y, s_gL + zn * D);
+          dl_z = -0.5 * wj * (lin_n - lin_p);
+          hp_stay = halfD * logw - 0.5 * wj * lin_p;   // per-spot part of plogLik if the label stays
+          hp_move = halfD * logw - 0.5 * wj * lin_n;   // ... if it moves (:1035, :1048)
+        }
+        // ---- sequential label updates inside each parent: r = 0..S-1, neighbour labels live (:984,:1029-1051)
+        for (int turn = 0; turn < S; turn++) {
+          if (active && r == turn) {
+            int deg = 0, cp = 0, cn = 0;
+            for (int ee = 0; ee < a.maxdeg; ee++) {
+              const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
+              if (nb >= 0) {
+                deg++;
+                const int zu = *((volatile uint8_t *) (a.z + nb));
+                cp += (zu == zk);
+                cn += (zu == zn);
+              }
+            }
+            double pot_p = 0.0, pot_n = 0.0;
+            if (deg) {
+              pot_p = a.gamma / deg * 2 * cp;
+              pot_n = a.gamma / deg * 2 * cn;
+            }
+            const double prob = exp((pot_n - pot_p) + dl_z);
+            if (prob != prob) atomicExch(a.err, BSB_DEVERR_NUMERIC);
+            const bool upd = prob >= 1.0 ? true : sample_two(prob, u_acc_z);
+            if (upd) {
+              a.z[si] = (uint8_t) zn;
+              zfinal = zn;
+              hp_acc += hp_move;
+            } else {
+              hp_acc += hp_stay;
+            }
+            __threadfence_block();
+          }
+          __syncwarp();
+        }
+        if (ADAPT && active && r == 0) a.nacc[ip] = nacc_new;
+      }
+      // ---- stage sqrt(w) y and fold the statistics of this pass -----------------------------------
+      {
+        const double sw = active ? sqrt(wj) : 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) tile[c * kTileLd + tid] = active ? sw * y[c] : 0.0;
+        sws[tid] = sw;
+        wvs[tid] = active ? wj : 0.0;
+        zs[tid] = (uint8_t) (active ? zfinal : 255);
+      }
+      __syncthreads();
+      tile_accumulate<D>(acc, a.SL, tile, sws, wvs, zs, true, false, tid);
+      __syncthreads();
+    }
+    block_reduce2(hp_acc, nacc_y, red, tid);
+    if (tid == 0) { acc[a.SL.hp] = hp_acc; acc[a.SL.nacc] = nacc_y; }
+    __syncthreads();
+    double *out = a.partials + (size_t) a.seg_slot[seg] * E;
+    for (int e2 = tid; e2 < E; e2 += kBlock) out[e2] = acc[e2];
+    __syncthreads();
+  }
+}
+
+size_t deconv_smem(const DeconvArgs &a) {
+  return deconv_smem_layout(BSB_D, a.PL.q, BSB_D * (BSB_D + 1) / 2, a.SL.E).bytes;
+}
+
+void launch_deconv(const DeconvArgs &a, int grid, cudaStream_t s) {
+  constexpr int D = BSB_D;
+  const size_t smem = deconv_smem(a);
+  static size_t attr0 = 0, attr1 = 0;
+  if (a.adaptive) {
+    if (smem > attr1) { cudaFuncSetAttribute(k_deconv<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); attr1 = smem; }
+    k_deconv<D, true><<<grid, kBlock, smem, s>>>(a);
+  } else {
+    if (smem > attr0) { cudaFuncSetAttribute(k_deconv<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); attr0 = smem; }
+    k_deconv<D, false><<<grid, kBlock, smem, s>>>(a);
+  }
+}
+
+KernelRegistrar reg(BSB_D, KernelsForD{nullptr, nullptr, nullptr, nullptr, launch_deconv, deconv_smem});
+
+}   // namespace
+}   // namespace bsb

@@ -1,0 +1,40 @@
+// kernels.hpp -- host-visible launchers of the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layout.hpp"
+
+namespace bsb {
+
+struct LoglikArgs {
+  const double *Y;      // n x d col-major (device)
+  int64_t n;
+  int q, nl;
+  const double *mu;     // q x d row-major
+  const double *rooti;  // nl x d x d col-major upper-triangular factor applied to (y - mu)
+  const double *logdet; // nl
+  const double *w;      // n or nullptr
+  int transposed;       // 0: z = R (y-mu)  (Q1 / precision form); 1: z = (y-mu) R (gallery original)
+  double *out;          // n x q col-major
+};
+
+struct DeconvArgs;   // deconv_kernels.cuh
+
+// Per-dimension kernel table: every kernel that keeps a spot's d PCs in registers is instantiated
+// once per d (1..kMaxD) in its own translation unit (sweep_kernels.cu with -DBSB_D=d).
+struct KernelsForD {
+  void (*sweep)(int tdist, int vvv, const SweepArgs &a, int grid, cudaStream_t s);
+  size_t (*sweep_smem)(int tdist, int vvv, const SweepArgs &a);
+  int (*sweep_max_blocks_per_sm)(int tdist, int vvv, size_t smem);
+  void (*loglik)(const LoglikArgs &a, cudaStream_t s);
+  void (*deconv)(const DeconvArgs &a, int grid, cudaStream_t s);
+  size_t (*deconv_smem)(const DeconvArgs &a);
+};
+KernelsForD *kernel_table();   // kMaxD + 1 entries, index = d; null pointers where not built
+struct KernelRegistrar {
+  KernelRegistrar(int d, const KernelsForD &k);
+};
+
+void launch_param(const ParamArgs &a, cudaStream_t stream);
+
+}   // namespace bsb

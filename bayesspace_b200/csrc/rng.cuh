@@ -1,0 +1,123 @@
+// rng.cuh -- counter-based randomness of the samplers (device side).
+//
+// Every variate is a pure function of (seed; purpose, index, iteration, slot): Philox4x32-10 with
+// counter = (index, slot, iteration, purpose) and key = seed.  A draw therefore belongs to "spot j
+// at iteration i", not to a position in a serial stream, which makes chains independent of the
+// colour schedule's launch geometry and of the number of GPUs (BASELINE.json north_star).
+// The reference draws from R's global Mersenne-Twister under Rcpp::RNGScope
+// (src/RcppExports.cpp:19); stream compatibility with it is not a goal.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsb {
+
+enum Purpose : uint32_t {
+  P_MU = 1,          // index = cluster k; normals m = 0..d-1            (rmvnorm, src/cluster.cpp:257)
+  P_WISH_NORM = 2,   // index = cluster k (0 if shared); m = i(i-1)/2+j  (rwish off-diagonals, :269)
+  P_WISH_CHI = 3,    // index = k*1024 + i; gamma attempts               (rwish diagonal)
+  P_SPOT_U = 4,      // index = spot; slot 0 = (u_proposal, u_accept)    (sample(), :278,304)
+  P_SPOT_GAMMA = 5,  // index = spot; gamma attempts for w               (R::rgamma, :518)
+  P_ERR = 6,         // index = subspot; normal m = column               (rmvnorm, :905)
+  P_SPOT_YACC = 7    // index = parent spot; slot 0 = u for the Y move   (sample(), :975)
+};
+
+struct Key {
+  uint32_t k0, k1;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               Key key) {
+  uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
+  const unsigned long long x = ((unsigned long long) hi << 32) | lo;
+  return ((double) (x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void rng_uniform2(Key key, uint32_t purpose, uint32_t index,
+                                             uint32_t iter, uint32_t slot, double &u0, double &u1) {
+  const uint4 o = philox4x32_10(index, slot, iter, purpose, key);
+  u0 = u53(o.x, o.y);
+  u1 = u53(o.z, o.w);
+}
+
+// Box-Muller pair.
+__device__ __forceinline__ void rng_normal2(Key key, uint32_t purpose, uint32_t index, uint32_t iter,
+                                            uint32_t slot, double &n0, double &n1) {
+  double u0, u1;
+  rng_uniform2(key, purpose, index, iter, slot, u0, u1);
+  const double r = sqrt(-2.0 * log(u0));
+  double s, c;
+  sincospi(2.0 * u1, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+__device__ __forceinline__ double rng_normal(Key key, uint32_t purpose, uint32_t index, uint32_t iter,
+                                             uint32_t m) {
+  double a, b;
+  rng_normal2(key, purpose, index, iter, m >> 1, a, b);
+  return (m & 1u) ? b : a;
+}
+
+// First Box-Muller output only (the gamma sampler needs one normal per attempt).
+__device__ __forceinline__ double rng_normal_first(Key key, uint32_t purpose, uint32_t index,
+                                                   uint32_t iter, uint32_t slot) {
+  double u0, u1;
+  rng_uniform2(key, purpose, index, iter, slot, u0, u1);
+  return sqrt(-2.0 * log(u0)) * cospi(2.0 * u1);
+}
+
+// Gamma(shape, scale) by Marsaglia & Tsang (2000); shape < 1 boosted by u^(1/shape).
+// Stand-in for R::rgamma (src/cluster.cpp:518,660,1007) and R::rchisq inside RcppDist::rwish.
+__device__ __forceinline__ double rng_gamma(Key key, uint32_t purpose, uint32_t index, uint32_t iter,
+                                            double shape, double scale) {
+  if (!(shape > 0.0) || !(scale > 0.0)) return __longlong_as_double(0x7ff8000000000000ll);
+  double boost = 1.0, a = shape;
+  if (a < 1.0) {
+    double u0, u1;
+    rng_uniform2(key, purpose, index, iter, 0x80000000u, u0, u1);
+    boost = pow(u0, 1.0 / a);
+    a += 1.0;
+  }
+  const double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+  for (uint32_t t = 0; t < 0x3fffffffu; t++) {
+    const double x = rng_normal_first(key, purpose, index, iter, 2u * t);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u, u_unused;
+    rng_uniform2(key, purpose, index, iter, 2u * t + 1u, u, u_unused);
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return dd * v * scale * boost;
+    if (log(u) < 0.5 * x2 + dd * (1.0 - v + log(v))) return dd * v * scale * boost;
+  }
+  return __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// Rcpp sugar sample(x, 1, TRUE, {1-p, p}): probabilities sorted descending, cumulative inversion
+// with one uniform.  True when the second element ("new") is picked.
+__device__ __forceinline__ bool sample_two(double p_new, double u) {
+  return (p_new >= 0.5) ? (u <= p_new) : (u > 1.0 - p_new);
+}
+
+// Rcpp sugar sample(qlessk, 1): x[floor(len*u)] over the labels without the current one, ascending.
+// Labels here are 0-based.
+__device__ __forceinline__ int propose_label(int z_prev, int q, double u) {
+  int t = (int) floor((double) (q - 1) * u);
+  if (t > q - 2) t = q - 2;
+  return (t < z_prev) ? t : t + 1;
+}
+
+}   // namespace bsb

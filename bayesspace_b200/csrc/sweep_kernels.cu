@@ -1,0 +1,307 @@
+// sweep_kernels.cu -- the z / w sweep of the four cluster samplers and the spot x cluster
+// log-density probe, instantiated for ONE dimension d = BSB_D per translation unit (a spot's PCs
+// live in registers, so d must be a compile-time constant).
+//
+// k_sweep<D, TDIST, VVV> replaces the sequential per-spot loops of
+//   iterate        /root/reference/src/cluster.cpp:272-307
+//   iterate_vvv    :392-430      iterate_t  :507-553      iterate_t_vvv  :646-695
+// by a chromatic scan: one launch per colour class, one thread per spot, and fuses into the same
+// pass the sufficient statistics the NEXT iteration's mu / lambda updates need
+// (:248-253, :261-265, :482-486, :500), so Y is read once per sweep.
+//
+// Differences from the reference's arithmetic, all exact in real arithmetic:
+//  * the covariance is factorised once per iteration in k_param, not twice per spot (:91);
+//  * shared precision: the quadratic form is expanded, q(y, mu_k) = y^T M y - 2 y^T (M mu_k)
+//    + mu_k^T M mu_k.  y^T M y cancels in the MH ratio; its sum over spots (needed only by the
+//    plogLik diagnostic, :305-307) is tr(M sum_j w_j y_j y_j^T), taken from the statistics;
+//  * Y is centred by its column means at upload (translation invariance), which keeps the
+//    expansion well conditioned.
+#include "kernels.hpp"
+#include "rng.cuh"
+#include "tile_stats.cuh"
+
+#ifndef BSB_D
+#error "compile with -DBSB_D=<d>"
+#endif
+
+namespace bsb {
+namespace {
+
+// Shared-memory carve-up of k_sweep (offsets in doubles).
+struct SweepSmem {
+  int g, c, gL, cL, PL, PM, logdet, tile, sws, wvs, acc, red, zs_bytes_off;
+  size_t bytes;
+};
+__host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int np, int E, bool tdist, bool vvv) {
+  SweepSmem s;
+  int o = 0;
+  s.g = o; o += q * D;
+  s.c = o; o += q;
+  s.gL = o; o += tdist ? q * D : 0;
+  s.cL = o; o += tdist ? q : 0;
+  s.PL = o; o += tdist ? nl * np : 0;
+  s.PM = o; o += vvv ? nl * np : 0;
+  s.logdet = o; o += vvv ? nl : 0;
+  o = (o + 1) & ~1;   // 16 B alignment of the tile
+  s.tile = o; o += D * kTileLd;
+  s.sws = o; o += kBlock;
+  s.wvs = o; o += kBlock;
+  s.acc = o; o += E;
+  s.red = o; o += 2 * (kBlock / 32);
+  s.zs_bytes_off = o * 8;
+  s.bytes = (size_t) o * 8 + kBlock;
+  return s;
+}
+
+template <int D, bool TDIST, bool VVV>
+__global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int NP = D * (D + 1) / 2;
+  const int tid = threadIdx.x;
+  const int q = a.PL.q, nl = a.PL.nl, E = a.SL.E;
+  const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV);
+  double *s_g = sm + L.g, *s_c = sm + L.c, *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL;
+  double *s_PM = sm + L.PM, *s_logdet = sm + L.logdet, *tile = sm + L.tile, *sws = sm + L.sws;
+  double *wvs = sm + L.wvs, *acc = sm + L.acc, *red = sm + L.red;
+  uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
+
+  const bool stats_only = a.flags & SW_STATS_ONLY, dry = a.flags & SW_DRY;
+  if (*a.err) return;
+  if (!stats_only) {
+    const double *P = a.params;
+    for (int e = tid; e < q * D; e += kBlock) s_g[e] = P[a.PL.g + e];
+    for (int e = tid; e < q; e += kBlock) s_c[e] = P[a.PL.c + e];
+    if (TDIST) {
+      for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
+      for (int e = tid; e < q; e += kBlock) s_cL[e] = P[a.PL.cL + e];
+      for (int e = tid; e < nl * NP; e += kBlock) s_PL[e] = P[a.PL.PL + e];
+    }
+    if (VVV) {
+      for (int e = tid; e < nl * NP; e += kBlock) s_PM[e] = P[a.PL.PM + e];
+      for (int e = tid; e < nl; e += kBlock) s_logdet[e] = P[a.PL.logdet + e];
+    }
+  }
+  const Key key{a.key0, a.key1};
+  const uint32_t it = *a.iter + a.iter_add;
+  const double w_alpha = (double) ((D + 4) / 2);   // quirk Q2: integer division (src/cluster.cpp:508)
+  const double halfD = 0.5 * D;
+  const bool do_pairs = !(a.flags & SW_NO_PAIRS) && a.SL.nlT > 0;
+  const bool per_cluster_pairs = a.SL.nlT > 1;
+
+  __syncthreads();
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const int begin = a.seg_begin[seg], count = a.seg_count[seg];
+    for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    double hp_acc = 0.0, nacc = 0.0;
+
+    for (int base = 0; base < count; base += kBlock) {
+      const bool active = base + tid < count;
+      const int64_t j = (int64_t) begin + base + tid;
+      double y[D];
+      double wj = 1.0;
+      int zfinal = 255;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < D; c++) y[c] = a.Y[(size_t) c * a.ld + j];
+        const int zk = a.z[j];
+        zfinal = zk;
+        if (stats_only) {
+          if (TDIST) wj = a.w[j];
+        } else {
+          const uint32_t og = (uint32_t) a.orig[j];
+          double u_prop, u_acc;
+          rng_uniform2(key, P_SPOT_U, og, it, 0u, u_prop, u_acc);
+          const int zn = propose_label(zk, q, u_prop);
+          int deg = 0, cp = 0, cn = 0;
+          for (int e = 0; e < a.maxdeg; e++) {
+            const int32_t nb = a.ell[(size_t) e * a.ld + j];
+            if (nb >= 0) {
+              deg++;
+              const int zu = a.z[nb];
+              cn += (zu == zn);
+              if (a.flags & SW_Q3) cp += (a.orig[nb] == zk + 1);   // quirk Q3 (:404)
+              else cp += (zu == zk);
+            }
+          }
+          double pot_p = 0.0, pot_n = 0.0;
+          if (deg) {
+            pot_p = a.gamma / deg * 2 * cp;
+            pot_n = a.gamma / deg * 2 * cn;
+          }
+          double logw = 0.0;
+          if (TDIST) {
+            // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518, :655-660)
+            const double aL = quadform<D>(y, s_PL + (VVV ? zk * NP : 0));
+            const double bL = dotv<D>(y, s_gL + zk * D);
+            const double quad = aL - 2.0 * bL + s_cL[zk];
+            wj = rng_gamma(key, P_SPOT_GAMMA, og, it, w_alpha, 2.0 / (quad + 4.0));
+            logw = log(wj);
+          }
+          const double lin_p = s_c[zk] - 2.0 * dotv<D>(y, s_g + zk * D);
+          const double lin_n = s_c[zn] - 2.0 * dotv<D>(y, s_g + zn * D);
+          double delta, hp_part, hp_full = 0.0, hn_full = 0.0;
+          if (VVV) {
+            const double ap = quadform<D>(y, s_PM + zk * NP), an = quadform<D>(y, s_PM + zn * NP);
+            const double hp = pot_p + (s_logdet[zk] + halfD * logw - 0.5 * wj * (ap + lin_p));
+            const double hn = pot_n + (s_logdet[zn] + halfD * logw - 0.5 * wj * (an + lin_n));
+            delta = hn - hp;
+            hp_part = hp;
+            if (dry) {
+              hp_full = hp - halfD * 1.8378770664093454835606594728112;
+              hn_full = hn - halfD * 1.8378770664093454835606594728112;
+            }
+          } else {
+            delta = (pot_n - pot_p) - 0.5 * wj * (lin_n - lin_p);
+            hp_part = pot_p + halfD * logw - 0.5 * wj * lin_p;
+            if (dry) {
+              const double aM = quadform<D>(y, a.params + a.PL.PM);
+              const double cst = a.params[a.PL.logdet] - halfD * 1.8378770664093454835606594728112;
+              hp_full = pot_p + (cst + halfD * logw - 0.5 * wj * (aM + lin_p));
+              hn_full = pot_n + (cst + halfD * logw - 0.5 * wj * (aM + lin_n));
+            }
+          }
+          double prob = exp(delta);
+          if (prob > 1.0) prob = 1.0;
+          if (prob != prob) atomicExch(a.err, BSB_DEVERR_NUMERIC);   // NA probability (Rcpp sample() stops)
+          const bool accept = sample_two(prob, u_acc);
+          if (dry) {
+            a.dry_znew[og] = zn + 1;
+            a.dry_w[og] = wj;
+            a.dry_hp[og] = hp_full;
+            a.dry_hn[og] = hn_full;
+            a.dry_prob[og] = prob;
+            a.dry_acc[og] = accept ? 1 : 0;
+          } else {
+            if (accept) {
+              a.z[j] = (uint8_t) zn;
+              zfinal = zn;
+              nacc += 1.0;
+            }
+            if (TDIST) a.w[j] = wj;
+            hp_acc += hp_part;
+          }
+        }
+      }
+      if (dry) continue;
+      // ---- stage sqrt(w) y, then every thread folds its statistic roles over the tile ----------
+      {
+        const double sw = active ? sqrt(wj) : 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) tile[c * kTileLd + tid] = active ? sw * y[c] : 0.0;
+        sws[tid] = sw;
+        wvs[tid] = active ? wj : 0.0;
+        zs[tid] = (uint8_t) zfinal;
+      }
+      __syncthreads();
+      tile_accumulate<D>(acc, a.SL, tile, sws, wvs, zs, do_pairs, per_cluster_pairs, tid);
+      __syncthreads();
+    }
+    if (dry) continue;
+    // ---- block-reduce the scalar parts in a fixed order and publish the segment's record -------
+    block_reduce2(hp_acc, nacc, red, tid);
+    if (tid == 0) { acc[a.SL.hp] = hp_acc; acc[a.SL.nacc] = nacc; }
+    __syncthreads();
+    double *out = a.partials + (size_t) a.seg_slot[seg] * E;
+    for (int e = tid; e < E; e += kBlock) out[e] = acc[e];
+    __syncthreads();
+  }
+}
+
+template <bool TDIST, bool VVV>
+void launch_sweep_t(const SweepArgs &a, int grid, cudaStream_t s) {
+  constexpr int D = BSB_D;
+  const SweepSmem L = sweep_smem_layout(D, a.PL.q, a.PL.nl, D * (D + 1) / 2, a.SL.E, TDIST, VVV);
+  static size_t attr = 0;
+  if (L.bytes > attr) {
+    cudaFuncSetAttribute(k_sweep<D, TDIST, VVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.bytes);
+    attr = L.bytes;
+  }
+  k_sweep<D, TDIST, VVV><<<grid, kBlock, L.bytes, s>>>(a);
+}
+
+void launch_sweep(int tdist, int vvv, const SweepArgs &a, int grid, cudaStream_t s) {
+  if (tdist) { if (vvv) launch_sweep_t<true, true>(a, grid, s); else launch_sweep_t<true, false>(a, grid, s); }
+  else { if (vvv) launch_sweep_t<false, true>(a, grid, s); else launch_sweep_t<false, false>(a, grid, s); }
+}
+
+size_t sweep_smem(int tdist, int vvv, const SweepArgs &a) {
+  return sweep_smem_layout(BSB_D, a.PL.q, a.PL.nl, BSB_D * (BSB_D + 1) / 2, a.SL.E, tdist, vvv).bytes;
+}
+
+int sweep_max_blocks(int tdist, int vvv, size_t smem) {
+  int nb = 0;
+  constexpr int D = BSB_D;
+  if (tdist) {
+    if (vvv) { cudaFuncSetAttribute(k_sweep<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+               cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, true, true>, kBlock, smem); }
+    else { cudaFuncSetAttribute(k_sweep<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, true, false>, kBlock, smem); }
+  } else {
+    if (vvv) { cudaFuncSetAttribute(k_sweep<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+               cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, false, true>, kBlock, smem); }
+    else { cudaFuncSetAttribute(k_sweep<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, false, false>, kBlock, smem); }
+  }
+  return nb;
+}
+
+// ---- K3: spot x cluster log-density probe (dmvnrm_arma_fast / dmvnrm_prec_arma_fast applied to
+// every (spot, cluster) pair), direct triangular form as at src/cluster.cpp:96-101, :122-127 ------
+template <int D>
+__global__ void __launch_bounds__(kBlock) k_loglik(const LoglikArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x;
+  const int q = a.q, nl = a.nl;
+  double *s_R = sm, *s_mu = s_R + nl * D * D, *s_ld = s_mu + q * D;
+  for (int e = tid; e < nl * D * D; e += kBlock) s_R[e] = a.rooti[e];
+  for (int e = tid; e < q * D; e += kBlock) s_mu[e] = a.mu[e];
+  for (int e = tid; e < nl; e += kBlock) s_ld[e] = a.logdet[e];
+  __syncthreads();
+  for (int64_t j = (int64_t) blockIdx.x * kBlock + tid; j < a.n; j += (int64_t) gridDim.x * kBlock) {
+    double y[D];
+#pragma unroll
+    for (int c = 0; c < D; c++) y[c] = a.Y[(size_t) c * a.n + j];
+    const double wj = a.w ? a.w[j] : 1.0;
+    const double lw = a.w ? 0.5 * D * log(wj) : 0.0;
+    for (int k = 0; k < q; k++) {
+      const double *R = s_R + (nl > 1 ? k : 0) * D * D;
+      double x[D];
+#pragma unroll
+      for (int c = 0; c < D; c++) x[c] = y[c] - s_mu[k * D + c];
+      double dot = 0.0;
+      if (!a.transposed) {
+#pragma unroll
+        for (int i = 0; i < D; i++) {   // inplace_tri_mat_mult_t (src/cluster.cpp:68-78)
+          double t = 0.0;
+#pragma unroll
+          for (int jj = i; jj < D; jj++) t += R[jj * D + i] * x[jj];
+          dot += t * t;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < D; jj++) {
+          double t = 0.0;
+#pragma unroll
+          for (int i = 0; i <= jj; i++) t += x[i] * R[jj * D + i];
+          dot += t * t;
+        }
+      }
+      a.out[(size_t) k * a.n + j] =
+          (s_ld[nl > 1 ? k : 0] + lw - 0.5 * D * 1.8378770664093454835606594728112) - 0.5 * wj * dot;
+    }
+  }
+}
+
+void launch_loglik(const LoglikArgs &a, cudaStream_t s) {
+  constexpr int D = BSB_D;
+  const size_t smem = sizeof(double) * ((size_t) a.nl * D * D + (size_t) a.q * D + a.nl);
+  cudaFuncSetAttribute(k_loglik<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  const int grid = (int) std::min<int64_t>((a.n + kBlock - 1) / kBlock, 148 * 8);
+  k_loglik<D><<<grid > 0 ? grid : 1, kBlock, smem, s>>>(a);
+}
+
+KernelRegistrar reg(BSB_D, KernelsForD{launch_sweep, sweep_smem, sweep_max_blocks, launch_loglik, nullptr, nullptr});
+
+}   // namespace
+}   // namespace bsb

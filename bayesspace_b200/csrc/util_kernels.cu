@@ -1,0 +1,152 @@
+// util_kernels.cu -- staging / bookkeeping kernels shared by the samplers (dimension-agnostic).
+#include "util_kernels.hpp"
+
+#include "smallmat.cuh"
+
+namespace bsb {
+
+std::atomic<long long> g_launches{0};
+
+// Column means of an n x d column-major matrix in a fixed (grid-independent) summation order:
+// one CTA per column, 256 strided partial sums, then a fixed tree.
+__global__ void __launch_bounds__(256) k_colmeans(const double *Y, int64_t n, double *ybar) {
+  __shared__ double red[256];
+  const double *col = Y + (size_t) blockIdx.x * n;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += 256) s += col[j];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ybar[blockIdx.x] = red[0] / (double) n;
+}
+
+// Yp[c][i] = Y[c][orig[i]] - ybar[c]   (gather into internal order + centring)
+__global__ void k_permute_center(const double *Y, int64_t src_ld, int64_t count, int d, const int32_t *orig,
+                                 const double *ybar, double *Yp, int64_t dst_ld) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t o = orig[i];
+  for (int c = 0; c < d; c++) Yp[(size_t) c * dst_ld + i] = Y[(size_t) c * src_ld + o] - ybar[c];
+}
+
+// Snapshot of the labels / weights in the caller's spot order (src/cluster.cpp:313, :559-560).
+__global__ void k_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n,
+                           int32_t *z_out, double *w_out) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t o = orig[i];
+  z_out[o] = (int32_t) z[i] + 1;
+  if (w_out) w_out[o] = w[i];
+}
+
+// Y snapshot for the deconvolution sampler: out[c][orig[i]] = Yp[c][i] + ybar[c]
+__global__ void k_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, const int32_t *orig,
+                             const double *ybar, double *out, int64_t dst_ld) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t o = orig[i];
+  for (int c = 0; c < d; c++) out[(size_t) c * dst_ld + o] = Yp[(size_t) c * src_ld + i] + ybar[c];
+}
+
+// running mean of Y snapshots: mean += (Y - mean) / count   (R/spatialEnhance.R:441)
+__global__ void k_running_mean(const double *snap, double *mean, int64_t len, double inv_count) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) mean[i] += (snap[i] - mean[i]) * inv_count;
+}
+
+// Level 1 of the two-level statistics reduction when there are many segments: one thread per
+// (group, entry), sequential over the group's slots (fixed order).
+__global__ void k_reduce_groups(const double *partials, const int32_t *group_start, int E, double *gsum) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+  if (e >= E) return;
+  double s = 0.0;
+  for (int slot = group_start[g]; slot < group_start[g + 1]; slot++) s += partials[(size_t) slot * E + e];
+  gsum[(size_t) g * E + e] = s;
+}
+
+// rooti / logdet per matrix for the log-density probe (one warp per matrix):
+// form 0: mat = Sigma  -> rooti = inv(chol(Sigma))   (src/cluster.cpp:91-92)
+// form 1: mat = Lambda -> rooti = chol(Lambda)       (:117-118)
+__global__ void k_factor(const double *mat, int d, int form, double *rooti, double *logdet, int *err) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x, k = blockIdx.x;
+  double *A = sm, *R = A + d * d, *T = R + d * d;
+  for (int e = lane; e < d * d; e += 32) A[e] = mat[(size_t) k * d * d + e];
+  __syncwarp();
+  bool ok = warp_chol_upper(A, R, d, lane);
+  const double *out = R;
+  if (form == 0) {
+    warp_inv_upper(R, T, d, lane);
+    out = T;
+  }
+  for (int e = lane; e < d * d; e += 32) rooti[(size_t) k * d * d + e] = out[e];
+  if (lane == 0) {
+    double ld = 0.0;
+    for (int i = 0; i < d; i++) ld += log(out[(size_t) i * d + i]);
+    logdet[k] = ld;
+    if (!ok) atomicExch(err, BSB_DEVERR_NUMERIC);
+  }
+}
+
+// Scatter about the cluster means from the moment sums (the identity k_param uses), for the
+// sufficient-statistics probe: S = T - sum_k (mu_k s_k^T + s_k mu_k^T - n_k mu_k mu_k^T).
+__global__ void k_scatter_probe(const double *stats, StatLayout SL, const double *mu, int nl, double *S) {
+  const int d = SL.d, q = SL.q, np = SL.np;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nl * d * d; idx += gridDim.x * blockDim.x) {
+    const int kk = idx / (d * d), e = idx % (d * d), ia = e % d, ib = e / d;
+    const int lo = ia < ib ? ia : ib, hi = ia < ib ? ib : ia;
+    double s = stats[SL.T + (size_t) (SL.nlT > 1 ? kk : 0) * np + (lo * d - lo * (lo - 1) / 2 + (hi - lo))];
+    const int k0 = nl > 1 ? kk : 0, k1 = nl > 1 ? kk + 1 : q;
+    for (int k = k0; k < k1; k++) {
+      const double ma = mu[k * d + ia], mb = mu[k * d + ib];
+      const double sa = stats[SL.sk + k * d + ia], sb = stats[SL.sk + k * d + ib];
+      s -= ma * sb + sa * mb - stats[SL.nk + k] * ma * mb;
+    }
+    S[idx] = s;
+  }
+}
+
+void launch_colmeans(const double *Y, int64_t n, int d, double *ybar, cudaStream_t s) {
+  k_colmeans<<<d, 256, 0, s>>>(Y, n, ybar);
+  g_launches++;
+}
+void launch_permute_center(const double *Y, int64_t src_ld, int64_t count, int d, const int32_t *orig,
+                           const double *ybar, double *Yp, int64_t dst_ld, cudaStream_t s) {
+  k_permute_center<<<(unsigned) ((count + 255) / 256), 256, 0, s>>>(Y, src_ld, count, d, orig, ybar, Yp, dst_ld);
+  g_launches++;
+}
+void launch_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n, int32_t *z_out,
+                     double *w_out, cudaStream_t s) {
+  k_snapshot<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(z, w, orig, n, z_out, w_out);
+  g_launches++;
+}
+void launch_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, const int32_t *orig,
+                       const double *ybar, double *out, int64_t dst_ld, cudaStream_t s) {
+  k_snapshot_Y<<<(unsigned) ((count + 255) / 256), 256, 0, s>>>(Yp, src_ld, count, d, orig, ybar, out, dst_ld);
+  g_launches++;
+}
+void launch_running_mean(const double *snap, double *mean, int64_t len, double inv_count, cudaStream_t s) {
+  k_running_mean<<<(unsigned) ((len + 255) / 256), 256, 0, s>>>(snap, mean, len, inv_count);
+  g_launches++;
+}
+void launch_reduce_groups(const double *partials, const int32_t *group_start, int ngroups, int E,
+                          double *gsum, cudaStream_t s) {
+  dim3 grid((E + 127) / 128, ngroups);
+  k_reduce_groups<<<grid, 128, 0, s>>>(partials, group_start, E, gsum);
+  g_launches++;
+}
+void launch_factor(const double *mat, int nl, int d, int form, double *rooti, double *logdet, int *err,
+                   cudaStream_t s) {
+  k_factor<<<nl, 32, 3 * (size_t) d * d * sizeof(double), s>>>(mat, d, form, rooti, logdet, err);
+  g_launches++;
+}
+void launch_scatter_probe(const double *stats, const StatLayout &SL, const double *mu, int nl, double *S,
+                          cudaStream_t s) {
+  k_scatter_probe<<<8, 256, 0, s>>>(stats, SL, mu, nl, S);
+  g_launches++;
+}
+
+}   // namespace bsb

@@ -1,0 +1,245 @@
+/* bsb200.h -- C ABI of libbsb200.so: the B200-native replacement for the MCMC sampler hot path of
+ * BayesSpace (reference: /root/reference, R package v1.15.3).
+ *
+ * Every entry point below replaces one symbol the reference registers for R's .Call interface
+ * (src/RcppExports.cpp:166-175) or one helper those symbols call.  The reference-side binding (an
+ * Rcpp shim that re-exports _BayesSpace_iterate* on top of this header) is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are caller-owned HOST memory unless stated;
+ *   - matrices are column-major exactly as R stores them (Y is n x d, lambda0 is d x d);
+ *   - labels are 1-based (as in R), neighbour ids are 0-based (as df_j is handed to C++,
+ *     R/spatialCluster.R:289);
+ *   - adjacency crosses the boundary as CSR: int64 ptr[n+1], int32 idx[nnz];
+ *   - outputs are snapshot-major: snapshot r (r = 0 .. nrep/thin) is contiguous;
+ *   - every function returns BSB200_OK (0) or a negative error code; bsb200_last_error() holds the
+ *     message the reference would have raised as an R error (thread-local);
+ *   - there is no CPU fallback: sampler and probe calls fail with BSB200_ERR_CUDA when no sm_100
+ *     device is usable.
+ */
+#ifndef BSB200_H
+#define BSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSB200_VERSION 100 /* 0.1.0 */
+
+enum {
+  BSB200_OK = 0,
+  BSB200_ERR_INVALID = -1,     /* "Invalid arguments!" (src/cluster.cpp:173) and argument checks  */
+  BSB200_ERR_NEIGHBORS = -2,   /* "Error in finding neighbors of subspots!" (src/cluster.cpp:208)  */
+  BSB200_ERR_PARSE = -3,       /* "Unconvertable value" / "Value out of range" (src/utils.h:39-41) */
+  BSB200_ERR_BUFFER = -4,      /* output capacity too small; required size is reported             */
+  BSB200_ERR_CUDA = -5,        /* CUDA runtime failure or no usable device                          */
+  BSB200_ERR_NUMERIC = -6,     /* NA in a probability vector / Wishart df <= 0 / not pos. definite  */
+                               /* (the reference errors inside sample() or chol())       */
+  BSB200_ERR_UNSUPPORTED = -7, /* d > 32, q > 255, degree > 16, ...                                 */
+  BSB200_ERR_CANCELLED = -8    /* bsb200_cancel() seen at a thin boundary (rows after it are zero)  */
+};
+
+enum { BSB200_MODEL_NORMAL = 0, BSB200_MODEL_T = 1 };
+enum { BSB200_PRECISION_EQUAL = 0, BSB200_PRECISION_VARIABLE = 1 };
+enum { BSB200_PLATFORM_VISIUM = 0, BSB200_PLATFORM_SQUARE = 1 /* "VisiumHD" and "ST" */ };
+enum { BSB200_METRIC_MANHATTAN = 0, BSB200_METRIC_EUCLIDEAN = 1 };
+
+/* Reference quirks reproduced by default. */
+#define BSB200_COMPAT_Q1 1u /* covariance-form density uses (R R^T)^-1, src/cluster.cpp:69-99     */
+#define BSB200_COMPAT_Q3 4u /* iterate_vvv compares neighbour indices to the label, :404          */
+#define BSB200_COMPAT_REFERENCE (BSB200_COMPAT_Q1 | BSB200_COMPAT_Q3)
+
+int bsb200_version(void);
+const char *bsb200_last_error(void);
+/* SIGTERM analogue (src/cluster.cpp:41-47, :1106-1107): running samplers stop at the next thin
+ * boundary.  The flag is cleared when a sampler call starts. */
+void bsb200_cancel(void);
+int bsb200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Neighbour construction (host).  Two-pass sizing: call with idx == NULL (or too small a capacity)
+ * to obtain *nnz, then again with a buffer of that many entries.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* .find_neighbors (R/spatialCluster.R:227-302): lattice neighbours from integer array coordinates;
+ * hex offsets (+-2,0),(+-1,+-1) or square offsets (0,+-1),(+-1,0); ascending by spot index. */
+int bsb200_neighbors_lattice(const int32_t *array_row, const int32_t *array_col, int64_t n,
+                             int32_t platform, int64_t *ptr, int32_t *idx, int64_t cap, int64_t *nnz);
+
+/* find_neighbors (R/utils.R:13-26): 0 < dist <= radius, ascending.  positions: n x 2 col-major. */
+int bsb200_neighbors_radius(const double *positions, int64_t n, double radius, int32_t metric,
+                            int64_t *ptr, int32_t *idx, int64_t cap, int64_t *nnz);
+
+/* convert_neighbors (src/cluster.cpp:134-145) + str_split (src/utils.h:10-62) + Neighbor ctor
+ * (src/neighbor.h:67-80): n0 strings "a,b,c" with 1-based ids, NULL = NA -> 0-based CSR. */
+int bsb200_parse_neighbor_strings(const char *const *strings, int64_t n0, int64_t *ptr, int32_t *idx,
+                                  int64_t cap, int64_t *nnz);
+
+/* find_subspot_neighbors (src/cluster.cpp:161-215): candidates = all subspots of (neighbour spots
+ * ascending, then the own spot); kept when 1e-6 < Manhattan distance < dist; candidate order is
+ * preserved.  positions: n x 2 col-major, subspot s = r*n0 + j0. */
+int bsb200_subspot_neighbors(const double *positions, int64_t n, int64_t n0, const int64_t *spot_ptr,
+                             const int32_t *spot_idx, double dist, int64_t *ptr, int32_t *idx,
+                             int64_t cap, int64_t *nnz);
+
+/* convert_neighbors2mtx (src/cluster.cpp:147-159): n x 4 col-major, 1-based, zero padded. */
+int bsb200_neighbors_to_matrix4(const int64_t *ptr, const int32_t *idx, int64_t n, int64_t *out);
+
+/* Graph colouring used by the chromatic scan (no reference counterpart: the reference scans
+ * sequentially, src/cluster.cpp:275).  Greedy in index order on the symmetrised graph (self loops
+ * ignored), so that no spot ever reads the label of a spot of its own colour. */
+int bsb200_colour_graph(const int64_t *ptr, const int32_t *idx, int64_t n, int32_t *colour,
+                        int32_t *ncolours);
+
+/* Closed-form lattice colourings: square (row + col) mod 2; hex
+ * ((col - 3 row) / 2) mod 3, which needs col == row (mod 2) as on Visium. */
+int bsb200_colour_lattice(const int32_t *array_row, const int32_t *array_col, int64_t n,
+                          int32_t platform, int32_t *colour, int32_t *ncolours);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cluster samplers: iterate / iterate_vvv / iterate_t / iterate_t_vvv
+ * (src/cluster.cpp:217-321 / 323-444 / 446-568 / 570-710; R/RcppExports.R:4-18).
+ * (model, precision) selects the reference function exactly as cluster() does
+ * (R/spatialCluster.R:94-106).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bsb200_cluster_args {
+  int32_t model;     /* BSB200_MODEL_*      */
+  int32_t precision; /* BSB200_PRECISION_*  */
+  int64_t n;         /* spots               */
+  int32_t d;         /* PCs, 1..32          */
+  int32_t q;         /* clusters, 2..255    */
+  int32_t nrep;      /* loop runs i = 1 .. nrep-1 */
+  int32_t thin;
+  double gamma, alpha, beta;
+  const double *Y;         /* n x d col-major                                   */
+  const int64_t *nbr_ptr;  /* df_j as CSR (0-based ids)                          */
+  const int32_t *nbr_idx;
+  const int32_t *init;     /* n labels, 1-based                                  */
+  const double *mu0;       /* d                                                  */
+  const double *lambda0;   /* d x d                                              */
+  uint64_t seed;           /* Philox key; the R shim draws it from R's RNG      */
+  uint32_t compat;         /* BSB200_COMPAT_* bitmask                            */
+  int32_t device;          /* CUDA device ordinal                                */
+  const int32_t *colour;   /* optional n colours (0-based) from bsb200_colour_graph, or NULL */
+  int32_t ncolours;
+  int32_t reserved;
+} bsb200_cluster_args;
+
+/* nsnap = nrep/thin + 1 rows.  Any pointer may be NULL to skip that output. */
+typedef struct bsb200_cluster_out {
+  int32_t *z;       /* nsnap x n, 1-based                                               */
+  double *mu;       /* nsnap x (q*d), row-wise vectorised (mu_1,1..mu_1,d, mu_2,1..)    */
+  double *lambda;   /* nsnap x nl x (d*d) col-major; nl = 1 (equal) or q (variable)     */
+  double *weights;  /* nsnap x n (t model only)                                         */
+  double *plogLik;  /* nrep, [0] = NaN                                                  */
+  int32_t rows_done; /* out: snapshot rows written (== nsnap unless cancelled)          */
+  int32_t ncolours;  /* out: colour classes used by the chromatic scan                  */
+  double setup_ms;   /* out: host->device staging + graph setup, wall clock             */
+  double device_ms;  /* out: device time of the sampling loop (CUDA events)             */
+} bsb200_cluster_out;
+
+int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out);
+
+/* Resident-chain interface: the same sampler with state kept in HBM between calls.  bench.py uses
+ * it to time sweeps with inputs already on the device; bsb200_cluster() is create + run + destroy. */
+typedef struct bsb200_chain bsb200_chain;
+int bsb200_chain_create(const bsb200_cluster_args *args, bsb200_chain **chain);
+/* Advances `iters` iterations (continuing the iteration counter); device time in *device_ms. */
+int bsb200_chain_run(bsb200_chain *chain, int32_t iters, double *device_ms);
+/* As bsb200_chain_run but launches kernel by kernel with CUDA events around every z-sweep launch:
+ * sweep_ms = total time inside the sweep kernels, launches = number of sweep launches timed. */
+int bsb200_chain_profile(bsb200_chain *chain, int32_t iters, double *sweep_ms, int64_t *launches,
+                         double *param_ms);
+/* Current state in the caller's (original) spot order; NULL pointers are skipped.
+ * plogLik receives the values of all iterations run so far (length = iterations done + 1). */
+int bsb200_chain_state(bsb200_chain *chain, int32_t *z, double *weights, double *mu, double *lambda,
+                       double *plogLik, int64_t *iters_done);
+int bsb200_chain_destroy(bsb200_chain *chain);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t bsb200_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * State-level parity probes (evaluate one quantity of the sampler on a caller-supplied state).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Spot x cluster log-density, n x q col-major:
+ * form 0: dmvnrm_arma_fast(y_j, mu_k, sigma_k / w_j) (src/cluster.cpp:83-106, Q1 under compat);
+ * form 1: dmvnrm_prec_arma_fast(y_j, mu_k, mat_k * w_j) (:109-132).
+ * mu: q x d row-major; mat: nl x d x d col-major (nl = 1 or q); w: n or NULL. */
+int bsb200_eval_loglik(int32_t device, int32_t form, uint32_t compat, const double *Y, int64_t n,
+                       int32_t d, int32_t q, const double *mu, const double *mat, int32_t nl,
+                       const double *w, double *out);
+
+/* Sufficient statistics the mu / lambda updates consume (src/cluster.cpp:248-265, 482-500):
+ * nk[q] = sum_j w_j [z_j = k], sk[q x d] row-major = sum w_j y_j, scatter[nl x d x d] =
+ * sum w_j (y_j - mu_{z_j})(y_j - mu_{z_j})^T (pooled when nl == 1). */
+int bsb200_eval_suffstats(int32_t device, const double *Y, int64_t n, int32_t d, int32_t q,
+                          const int32_t *z, const double *w, const double *mu, int32_t nl,
+                          double *nk, double *sk, double *scatter);
+
+/* One dry sweep on the chain's current state: for every spot the proposal the chain would make at
+ * its next iteration and the two values the MH step compares (src/cluster.cpp:283-298), without
+ * changing the state.  All outputs are length n, original spot order. */
+int bsb200_chain_dry_sweep(bsb200_chain *chain, int32_t *z_new, double *w_new, double *h_prev,
+                           double *h_new, double *prob, int32_t *accepted);
+
+/* Keyed random variates exactly as the kernels draw them (u in (0,1), N(0,1), Gamma(shape, scale)):
+ * kind 0 uniform pair (count must be 2), 1 normals m0.., 2 gammas for index0.. */
+int bsb200_debug_rng(int32_t device, int32_t kind, uint64_t seed, uint32_t purpose, uint32_t index,
+                     uint32_t iter, uint32_t slot, double shape, double scale, int32_t count,
+                     double *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * iterate_deconv (src/cluster.cpp:742-1141; R/RcppExports.R:20-22)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bsb200_deconv_args {
+  const double *subspot_positions; /* n x 2 col-major                                   */
+  double dist;
+  const int64_t *spot_nbr_ptr;     /* parsed spot.neighbors (bsb200_parse_neighbor_strings) */
+  const int32_t *spot_nbr_idx;
+  const double *Y;                 /* n x d col-major, parent PCs replicated; NOT mutated (Q10) */
+  int32_t tdist;
+  int32_t nrep, thin;
+  int64_t n, n0;
+  int32_t d;
+  double gamma;
+  int32_t q;
+  const int32_t *init;             /* n labels, 1-based */
+  int32_t subspots;
+  int32_t verbose;
+  double jitter_scale;             /* 0 => adaptive (Robust Adaptive Metropolis) */
+  int32_t adapt_before;
+  double c;
+  const double *mu0;
+  const double *lambda0;
+  double alpha, beta;
+  int32_t thread_num;              /* accepted for signature parity; ignored */
+  uint64_t seed;
+  int32_t device;
+  int32_t reserved;
+} bsb200_deconv_args;
+
+typedef struct bsb200_deconv_out {
+  int32_t *z;       /* nsnap x n                                          */
+  double *mu;       /* nsnap x (q*d)                                      */
+  double *lambda;   /* nsnap x (d*d)                                      */
+  double *weights;  /* nsnap x n (ones for the normal model)              */
+  double *Y;        /* nsnap x (n x d col-major), or NULL                 */
+  double *Y_mean;   /* optional running mean of the Y snapshots r >= mean_from (n x d col-major) */
+  int32_t mean_from;
+  double *Ychange;  /* nrep, [0] = NaN                                    */
+  double *plogLik;  /* nrep, [0] = NaN                                    */
+  int64_t *df_j;    /* n x 4 col-major, 1-based zero padded               */
+  int32_t rows_done;
+  int32_t ncolours;
+  double setup_ms, device_ms;
+} bsb200_deconv_out;
+
+int bsb200_deconv(const bsb200_deconv_args *args, bsb200_deconv_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSB200_H */
