@@ -121,12 +121,13 @@ def test_mh_ratio_probe(bsb, oracle, fname, model, precision, name):
     dry = ch.dry_sweep()
     st2 = ch.state()
     assert np.array_equal(st["z"], st2["z"]) and st2["iters_done"] == 3      # dry run leaves the chain untouched
-    # parameters the dry sweep used = those of iteration 4: rerun the oracle to the same point
-    ref = getattr(oracle, fname)(*_args(w, csr, 5, 1), seed=SEED, order=order)
-    mu4 = ref["mu"][4].reshape(w.q, w.d)
-    lam4 = ref["lambda"][4]
+    # parameters the dry sweep used = those of iteration 4: rerun the oracle to the same point.
+    # With thin = 1 iteration i is stored in row i + 1 (row (i+1)/thin, src/cluster.cpp:310-313).
+    ref = getattr(oracle, fname)(*_args(w, csr, 6, 1), seed=SEED, order=order)
+    mu4 = ref["mu"][5].reshape(w.q, w.d)
+    lam4 = ref["lambda"][5]
     sig4 = np.array([np.linalg.inv(l) for l in lam4]) if precision == "variable" else np.linalg.inv(lam4)
-    assert np.array_equal(st["z"], ref["z"][3])
+    assert np.array_equal(st["z"], ref["z"][4])
     wts = dry["w"] if model == "t" else None
     hp, hn = oracle.h_values(fname, w.Y, csr, st["z"], wts, mu4, sig4, w.gamma, dry["z_new"])
     assert np.max(np.abs(dry["h_prev"] - hp) / np.abs(hp)) < 1e-9
