@@ -190,18 +190,20 @@ int subspot_neighbors(const double *pos, int64_t n, int64_t n0, const int64_t *s
   return BSB200_OK;
 }
 
-// Greedy colouring in index order on the symmetrised graph (self loops ignored).  Same-colour
-// spots never read each other's label, which is all the chromatic scan needs.
+// Colouring of the symmetrised graph (self loops ignored): same-colour spots never read each
+// other's label, which is all the chromatic scan needs.  DSATUR (Brelaz 1979) with ties broken by
+// degree, then index: exact on bipartite graphs (square lattices, subspot graphs: 2 colours) and it
+// finds the 3-colouring of triangulated hex lattices.  Deterministic.  Above 2M vertices the heap is
+// skipped in favour of plain greedy in index order (callers with lattices pass closed-form colours).
 int colour_graph(const int64_t *ptr, const int32_t *idx, int64_t n, std::vector<int32_t> &colour,
                  int32_t *ncolours) {
-  // reverse edges that are missing from the forward lists
-  std::vector<int64_t> rptr((size_t) n + 1, 0);
-  bool asym = false;
   for (int64_t i = 0; i < n; i++)
     for (int64_t e = ptr[i]; e < ptr[i + 1]; e++) {
       const int32_t j = idx[e];
       if (j < 0 || j >= n) return fail(BSB200_ERR_INVALID, "neighbour index %d out of range", (int) j);
     }
+  // reverse edges that are missing from the forward lists
+  bool asym = false;
   std::vector<std::vector<int32_t>> extra;
   for (int64_t i = 0; i < n; i++)
     for (int64_t e = ptr[i]; e < ptr[i + 1]; e++) {
@@ -214,18 +216,60 @@ int colour_graph(const int64_t *ptr, const int32_t *idx, int64_t n, std::vector<
         extra[(size_t) j].push_back((int32_t) i);
       }
     }
+  auto for_each_nb = [&](int64_t i, auto &&fn) {
+    for (int64_t e = ptr[i]; e < ptr[i + 1]; e++) if (idx[e] != i) fn(idx[e]);
+    if (asym) for (int32_t j : extra[(size_t) i]) fn(j);
+  };
   colour.assign((size_t) n, -1);
+  std::vector<uint64_t> mask((size_t) n, 0);   // colours seen among neighbours (first 64)
   int32_t nc = 0;
-  std::vector<uint8_t> used;
-  for (int64_t i = 0; i < n; i++) {
-    used.assign((size_t) nc + 1, 0);
-    auto mark = [&](int32_t j) { if (j != i && colour[(size_t) j] >= 0) used[(size_t) colour[(size_t) j]] = 1; };
-    for (int64_t e = ptr[i]; e < ptr[i + 1]; e++) mark(idx[e]);
-    if (asym) for (int32_t j : extra[(size_t) i]) mark(j);
+  auto lowest_free = [&](int64_t i) {
     int32_t c = 0;
-    while (c < nc && used[(size_t) c]) c++;
+    if (~mask[(size_t) i]) c = __builtin_ctzll(~mask[(size_t) i]);
+    else {   // more than 64 colours around a vertex: exact scan
+      std::vector<uint8_t> used((size_t) nc + 1, 0);
+      for_each_nb(i, [&](int32_t j) { if (colour[(size_t) j] >= 0) used[(size_t) colour[(size_t) j]] = 1; });
+      c = 64;
+      while (c < nc && used[(size_t) c]) c++;
+    }
+    return c;
+  };
+  auto assign = [&](int64_t i, int32_t c) {
     colour[(size_t) i] = c;
-    if (c == nc) nc++;
+    if (c >= nc) nc = c + 1;
+  };
+  if (n > 2000000) {
+    for (int64_t i = 0; i < n; i++) {
+      for_each_nb(i, [&](int32_t j) { if (colour[(size_t) j] >= 0 && colour[(size_t) j] < 64) mask[(size_t) i] |= 1ull << colour[(size_t) j]; });
+      assign(i, lowest_free(i));
+    }
+  } else {
+    std::vector<int32_t> deg((size_t) n, 0), sat((size_t) n, 0);
+    for (int64_t i = 0; i < n; i++) for_each_nb(i, [&](int32_t) { deg[(size_t) i]++; });
+    // max-heap on (saturation, degree, -index) with lazy invalidation
+    typedef std::pair<std::pair<int32_t, int32_t>, int32_t> Item;
+    std::vector<Item> heap;
+    heap.reserve((size_t) n * 2);
+    for (int64_t i = 0; i < n; i++) heap.push_back({{0, deg[(size_t) i]}, (int32_t) -i});
+    std::make_heap(heap.begin(), heap.end());
+    while (!heap.empty()) {
+      std::pop_heap(heap.begin(), heap.end());
+      const Item it = heap.back();
+      heap.pop_back();
+      const int64_t i = -it.second;
+      if (colour[(size_t) i] >= 0 || it.first.first != sat[(size_t) i]) continue;   // stale entry
+      const int32_t c = lowest_free(i);
+      assign(i, c);
+      for_each_nb(i, [&](int32_t j) {
+        if (colour[(size_t) j] >= 0 || c >= 64) return;
+        if (!(mask[(size_t) j] & (1ull << c))) {
+          mask[(size_t) j] |= 1ull << c;
+          sat[(size_t) j]++;
+          heap.push_back({{sat[(size_t) j], deg[(size_t) j]}, (int32_t) -j});
+          std::push_heap(heap.begin(), heap.end());
+        }
+      });
+    }
   }
   if (ncolours) *ncolours = nc;
   return BSB200_OK;
@@ -252,6 +296,55 @@ void bsb200_cancel(void) { g_cancel.store(1); }
 int bsb200_neighbors_lattice(const int32_t *array_row, const int32_t *array_col, int64_t n,
                              int32_t platform, int64_t *ptr, int32_t *idx, int64_t cap, int64_t *nnz) {
   if (n < 0 || (n > 0 && (!array_row || !array_col))) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  if (platform != BSB200_PLATFORM_VISIUM && platform != BSB200_PLATFORM_SQUARE)
+    return fail(BSB200_ERR_INVALID, ".find_neighbors: Unsupported platform \"%d\".", platform);
+  // Fast path for compact lattices without duplicated coordinates (the Visium-HD / 10M-spot case):
+  // a dense (row, col) -> spot table and direct CSR emission, no per-spot allocations.
+  if (n > 0) {
+    static const int hx[6] = {-2, 2, -1, 1, -1, 1}, hy[6] = {0, 0, -1, -1, 1, 1};
+    static const int sx[4] = {0, 1, 0, -1}, sy[4] = {-1, 0, 1, 0};
+    const int no = platform == BSB200_PLATFORM_VISIUM ? 6 : 4;
+    const int *ox = platform == BSB200_PLATFORM_VISIUM ? hx : sx, *oy = platform == BSB200_PLATFORM_VISIUM ? hy : sy;
+    int32_t rmin = array_row[0], rmax = rmin, cmin = array_col[0], cmax = cmin;
+    for (int64_t j = 1; j < n; j++) {
+      rmin = std::min(rmin, array_row[j]); rmax = std::max(rmax, array_row[j]);
+      cmin = std::min(cmin, array_col[j]); cmax = std::max(cmax, array_col[j]);
+    }
+    const int64_t H = (int64_t) rmax - rmin + 1, W = (int64_t) cmax - cmin + 1;
+    bool dense = H * W <= 64 * n + 1024;
+    std::vector<int32_t> grid;
+    if (dense) {
+      grid.assign((size_t) (H * W), -1);
+      for (int64_t j = 0; j < n && dense; j++) {
+        int32_t &g = grid[(size_t) ((array_row[j] - rmin) * W + (array_col[j] - cmin))];
+        if (g >= 0) dense = false;
+        g = (int32_t) j;
+      }
+    }
+    if (dense) {
+      const bool fill = idx && ptr;
+      int64_t total = 0;
+      for (int64_t j = 0; j < n; j++) {
+        int32_t nb[6];
+        int cnt = 0;
+        for (int o = 0; o < no; o++) {
+          const int64_t r = (int64_t) array_row[j] + oy[o] - rmin, c = (int64_t) array_col[j] + ox[o] - cmin;
+          if (r < 0 || r >= H || c < 0 || c >= W) continue;
+          const int32_t u = grid[(size_t) (r * W + c)];
+          if (u >= 0) nb[cnt++] = u;
+        }
+        std::sort(nb, nb + cnt);
+        if (ptr) ptr[j] = total;
+        if (fill && total + cnt <= cap)
+          for (int e = 0; e < cnt; e++) idx[total + e] = nb[e];
+        total += cnt;
+      }
+      if (ptr) ptr[n] = total;
+      if (nnz) *nnz = total;
+      if ((idx || cap > 0) && cap < total) return fail(BSB200_ERR_BUFFER, "neighbour buffer too small: need %lld entries", (long long) total);
+      return BSB200_OK;
+    }
+  }
   std::vector<std::vector<int32_t>> adj;
   int rc = lattice_neighbors(array_row, array_col, n, platform, adj);
   return rc ? rc : emit_csr(adj, ptr, idx, cap, nnz);

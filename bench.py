@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- spot-updates/s of the MCMC sampler hot path on B200 (BASELINE.json metric).
+
+A "step" is one MCMC sweep (one pass of the hot path over every spot of the synthetic lattice):
+k_param + one chromatic z/w sweep launch per colour class.  Default workload = BASELINE config C5
+(10M-spot square lattice, t model, q=7, d=15): the largest single-GPU configuration, the only one
+whose state (1.2 GB of PCs) exceeds the 126 MB L2, i.e. the one on which "% of HBM peak" -- part of the
+metric -- is defined.  C2 (Visium, 4,992 spots) and C4 (700k bins) are reported in `other_workloads`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c2] [--impl reference]
+
+N > 1 is launched by the driver through torch.distributed.run; ranks run one independent chain each
+(the qTune / multi-chain mode of the north_star: no data-path collective, "scaling": "weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_NOTE = "8d + 4 (z read) + 4 (z write) + 4*deg (neighbour z) + 8 (w write, t model) bytes per spot-update"
+
+
+def algorithmic_bytes(d, mean_deg, tdist):
+    return 8.0 * d + 4 + 4 + 4.0 * mean_deg + (8 if tdist else 0)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7:
+                self.rows.append(f)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for f in self.rows:
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name):
+    import bayesspace_b200 as B
+    from bayesspace_b200 import synth
+    w = synth.make_workload(name)
+    _, csr = B.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
+    colour = B.colour_lattice(w.array_row, w.array_col, w.platform)
+    return w, csr, colour
+
+
+def chain_args(w, csr, nrep, thin):
+    return (w.Y, csr, nrep, thin, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0, w.alpha, w.beta)
+
+
+def subsample(w, csr, n_s):
+    """First n_s spots (whole lattice rows) of the workload with edges leaving the sample dropped."""
+    n_s = int(min(w.n, max(w.cols * 4, (n_s // w.cols) * w.cols)))
+    ptr = csr[0][:n_s + 1]
+    idx = csr[1][:ptr[-1]]
+    keep = idx < n_s
+    cs = np.concatenate([[0], np.cumsum(keep)]).astype(np.int64)
+    init = w.init[:n_s].copy()
+    for k in range(1, w.q + 1):
+        if not np.any(init == k):
+            init[k - 1] = k
+    return n_s, (cs[ptr], idx[keep].copy()), init
+
+
+def cpu_baseline(w, csr, budget_s=15.0, sweeps=2):
+    """Oracle (CPU restatement of the reference, single thread like the reference's cluster samplers)
+    on a bounded sample: the first rows of the same lattice."""
+    from oracle import oracle as O
+    fn = {("normal", "equal"): O.iterate, ("normal", "variable"): O.iterate_vvv, ("t", "equal"): O.iterate_t,
+          ("t", "variable"): O.iterate_t_vvv}[(w.model, w.precision)]
+
+    def run(n_s, nsw):
+        n_s, g, init = subsample(w, csr, n_s)
+        Y = w.Y[:n_s]
+        t0 = time.perf_counter()
+        fn(Y, g, nsw + 1, 100, n_s, w.d, w.gamma, w.q, init, Y.mean(axis=0), w.lambda0, w.alpha, w.beta, seed=1)
+        return n_s, time.perf_counter() - t0
+
+    n0, t = run(min(w.n, 4096), 1)
+    rate = n0 / t
+    n_s = int(min(w.n, max(4096, rate * budget_s / sweeps)))
+    n_s, t = run(n_s, sweeps)
+    return {"value": n_s * sweeps / t, "unit": "spot-updates/s", "cores": 1, "kind": "port",
+            "sample": "%d sweeps over the first %d spots (%d lattice rows) of the same workload, %.1f s" %
+                      (sweeps, n_s, n_s // w.cols, t)}, n_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bayesspace_b200 import synth
+    import bayesspace_b200 as B
+    w, csr, _ = build_workload(args.workload)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    # bounded sample sized so that K + W sweeps take about a minute on one host core
+    base, n_cal = cpu_baseline(w, csr, budget_s=3.0, sweeps=1)
+    rate = base["value"]
+    budget = 60.0
+    n_s = int(min(w.n, max(4 * w.cols, rate * budget / (K + W))))
+    from oracle import oracle as O
+    fn = {("normal", "equal"): O.iterate, ("normal", "variable"): O.iterate_vvv, ("t", "equal"): O.iterate_t,
+          ("t", "variable"): O.iterate_t_vvv}[(w.model, w.precision)]
+    n_s, g, init = subsample(w, csr, n_s)
+    Y = w.Y[:n_s]
+    a = lambda nsw: (Y, g, nsw + 1, 1000000, n_s, w.d, w.gamma, w.q, init, Y.mean(axis=0), w.lambda0, w.alpha, w.beta)
+    if W:
+        fn(*a(W), seed=1)
+    t0 = time.perf_counter()
+    fn(*a(K), seed=2)
+    t = time.perf_counter() - t0
+    val = n_s * K / t
+    sample = "%d sweeps over the first %d spots (%d lattice rows) of %s" % (K, n_s, n_s // w.cols, args.workload)
+    line = {"impl": "reference", "metric": "spot-updates/s", "value": val, "unit": "spot-updates/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(w, args.workload, sample=sample),
+            "cpu_baseline": {"value": val, "unit": "spot-updates/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "spot-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of the reference's sampler (oracle/ref_cpu.cpp, g++ -O2, 1 thread as in the "
+                    "reference's cluster samplers); the R/Rcpp reference itself cannot be built in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, name, **extra):
+    desc = {"c5": "C5: 10M-spot square lattice (3200 x 3125), t model, shared precision, q=7, d=15",
+            "c4": "C4: Visium-HD scale 837 x 837 square bins, t model, q=15, d=20",
+            "c2": "C2: Visium 78 x 64 hex lattice (4,992 spots), t model, q=7, d=15"}.get(name, name)
+    cfg = {"workload": desc, "n_spots": int(w.n), "d": int(w.d), "q": int(w.q), "model": w.model,
+           "precision": w.precision, "gamma": w.gamma, "l2_policy": "inputs larger than L2" if w.n * w.d * 8 > 126e6
+           else "state fits in L2 (latency-bound size; no flush: a chain re-reads its own state by construction)"}
+    cfg.update(extra)
+    return cfg
+
+
+def time_workload(B, w, csr, colour, K, W, device, with_profile=True):
+    thin = 100
+    nrep = W + 2 * K + 64
+    t0 = time.perf_counter()
+    ch = B.Chain(*chain_args(w, csr, nrep, thin), model=w.model, precision=w.precision, seed=149, device=device,
+                 colour=colour)
+    setup_s = time.perf_counter() - t0
+    ch.run(W)
+    l0 = B.kernel_launches()
+    ms = ch.run(K)
+    launches = B.kernel_launches() - l0
+    prof = ch.profile(min(K, 50)) if with_profile else None
+    ch.close()
+    return ms, launches, prof, setup_s
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import bayesspace_b200 as B
+    if B.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; bayesspace_b200 has no CPU fallback")
+    K, W = max(1, args.steps), max(3, args.warmup)
+    w, csr, colour = build_workload(args.workload)
+    mean_deg = len(csr[1]) / w.n
+    Bspot = algorithmic_bytes(w.d, mean_deg, w.model == "t")
+    peak, peak_src = measured_peak()
+
+    thin = 100
+    nrep = W + 2 * K + 64
+    ch = B.Chain(*chain_args(w, csr, nrep, thin), model=w.model, precision=w.precision, seed=149 + rank,
+                 device=local, colour=colour)
+    ch.run(W)
+    clocks = ClockSampler(local)
+    if dist:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks.start()
+    l0 = B.kernel_launches()
+    ms = ch.run(K)   # CUDA events on the library's stream around the K captured iterations
+    launches = B.kernel_launches() - l0
+    if dist:
+        import torch
+        torch.cuda.synchronize()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    prof = ch.profile(min(K, 50))
+    ck = clocks.stop()
+    ch.close()
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    value = world * w.n * K / (ms * 1e-3)
+    sweep_ms_per_launch = prof["sweep_ms"] / max(1, prof["sweep_launches"])
+    bytes_per_launch = Bspot * w.n / colour[1]
+    achieved = bytes_per_launch / (sweep_ms_per_launch * 1e-3) / 1e9
+    line = {"metric": "spot-updates/s", "value": value, "unit": "spot-updates/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(w, args.workload, parallelism="1 chain per GPU (replicas, no collective)"
+                                      if world > 1 else "single chain, 1 GPU",
+                                      sweeps_per_s=world * K / (ms * 1e-3), colours=colour[1]),
+            "roofline": {"bound": "hbm", "kernel": "k_sweep<%d,t,shared>" % w.d, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_spot_update": Bspot, "bytes_per_launch": bytes_per_launch,
+                         "avg_launch_ms": sweep_ms_per_launch, "formula": ALGO_NOTE,
+                         "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50))},
+            "gpu_launches": int(launches), "clocks": ck}
+    # ---- end to end through the C ABI with host buffers (bsb200_cluster: H2D, chain, snapshots D2H) ------
+    e2e_iters = args.e2e_iters
+    t0 = time.perf_counter()
+    out = B.cluster(w.Y, w.q, csr, init=w.init, model=w.model, precision=w.precision, mu0=w.mu0, lambda0=w.lambda0,
+                    gamma=w.gamma, alpha=w.alpha, beta=w.beta, nrep=e2e_iters + 1, thin=100, seed=7, device=local,
+                    colour=colour)
+    e2e_s = time.perf_counter() - t0
+    nsnap = (e2e_iters + 1) // 100
+    h2d = w.n * w.d * 8 + w.n * 4 + len(csr[1]) * 4 + (w.n + 1) * 8
+    d2h = nsnap * w.n * (4 + (8 if w.model == "t" else 0)) + (e2e_iters + 1) * 8
+    line["e2e"] = {"value": world * w.n * e2e_iters / e2e_s, "unit": "spot-updates/s",
+                   "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
+                   "call": "bsb200_cluster(nrep=%d, thin=100) with host buffers: wall clock of the whole call "
+                           "(host-side graph colouring/ordering, H2D, %d sweeps, %d snapshots D2H)" %
+                           (e2e_iters + 1, e2e_iters, nsnap),
+                   "wall_s": e2e_s, "setup_ms": out["_info"]["setup_ms"], "device_ms": out["_info"]["device_ms"]}
+    # ---- CPU baseline beside it (rank 0, bounded sample) ----------------------------------------------------
+    if not args.no_cpu:
+        cb, _ = cpu_baseline(w, csr)
+        line["cpu_baseline"] = cb
+    # ---- the other sizes the metric is quoted on -------------------------------------------------------------
+    if args.others and world == 1:
+        others = {}
+        for name in [x for x in ("c2", "c4") if x != args.workload]:
+            w2, csr2, col2 = build_workload(name)
+            k2 = 2000 if name == "c2" else 200
+            ms2, _, prof2, _ = time_workload(B, w2, csr2, col2, k2, 20, local)
+            b2 = algorithmic_bytes(w2.d, len(csr2[1]) / w2.n, True)
+            per_launch = prof2["sweep_ms"] / max(1, prof2["sweep_launches"])
+            others[name] = {"config": workload_config(w2, name), "spot_updates_per_s": w2.n * k2 / (ms2 * 1e-3),
+                            "sweeps_per_s": k2 / (ms2 * 1e-3), "us_per_iteration": 1e3 * ms2 / k2,
+                            "hbm_frac_sweep_kernel": (b2 * w2.n / col2[1]) / (per_launch * 1e-3) / 1e9 / peak}
+            if not args.no_cpu:
+                others[name]["cpu_baseline"], _ = cpu_baseline(w2, csr2, budget_s=8.0)
+        line["other_workloads"] = others
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c4", "c2"])
+    ap.add_argument("--e2e-iters", type=int, default=1000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", dest="others", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
