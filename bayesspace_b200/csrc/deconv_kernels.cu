@@ -24,21 +24,25 @@ namespace bsb {
 namespace {
 
 struct DeconvSmem {
-  int gL, cL, PL, tile, sws, wvs, acc, red, zs_bytes_off;
+  int gL, cL, PL, tile, sws, wvs, acc, accP, ct, red, zs_bytes_off, P;
   size_t bytes;
 };
 __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, int E) {
   DeconvSmem s;
+  const int DP = (D + 7) / 8 * 8, NT = DP / 8, NTILES = NT * (NT + 1) / 2;
   int o = 0;
   s.gL = o; o += q * D;
   s.cL = o; o += q;
   s.PL = o; o += np;
   o = (o + 1) & ~1;
-  s.tile = o; o += D * kTileLd;
+  s.tile = o; o += DP * kTileLd;
   s.sws = o; o += kBlock;
   s.wvs = o; o += kBlock;
   s.acc = o; o += E;
-  s.red = o; o += 2 * (kBlock / 32);
+  s.P = cluster_sum_parts(D, q);
+  s.accP = o; o += s.P * q * (D + 2);
+  s.ct = o; o += (kBlock / 32) * NTILES * 64;
+  s.red = o; o += 3 * (kBlock / 32);
   s.zs_bytes_off = o * 8;
   s.bytes = (size_t) o * 8 + kBlock;
   return s;
@@ -47,14 +51,16 @@ __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, i
 template <int D, bool ADAPT>
 __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NP = D * (D + 1) / 2;
+  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = a.PL.q, E = a.SL.E, S = a.S;
   const DeconvSmem L = deconv_smem_layout(D, q, NP, E);
   double *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL, *tile = sm + L.tile, *sws = sm + L.sws;
-  double *wvs = sm + L.wvs, *acc = sm + L.acc, *red = sm + L.red;
+  double *wvs = sm + L.wvs, *acc = sm + L.acc, *accP = sm + L.accP, *ct = sm + L.ct, *red = sm + L.red;
   uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
+  const int P = L.P;
   if (*a.err) return;
+  for (int e = tid; e < (DP - D) * kTileLd; e += kBlock) tile[D * kTileLd + e] = 0.0;   // padding rows of the tile
   if (!a.stats_only) {
     const double *P = a.params;
     for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
@@ -75,7 +81,12 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
+    double C[NTILES][2];
+#pragma unroll
+    for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
     double hp_acc = 0.0, nacc_y = 0.0;
+    LogProd lw;
 
     for (int base = 0; base < count; base += ppb) {
       const int pidx = base + warp * gpw + g;
@@ -203,11 +214,10 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
             }
           }
           // ---- t-model weight (:998-1008)
-          double logw = 0.0;
           if (a.tdist) {
             wj = rng_gamma(key, P_SPOT_GAMMA, sorig, it, w_alpha, 2.0 / (quad_old + 4.0));
             a.w[si] = wj;
-            logw = log(wj);
+            lw.mul(wj);   // (d/2) log w_j enters plogLik only: accumulated as a product, one log per segment
           }
           // ---- label proposal; the density part of the MH ratio is known before the scan (:1011-1027)
           double u_prop;
@@ -216,8 +226,8 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           const double lin_p = s_cL[zk] - 2.0 * b_old;
           const double lin_n = s_cL[zn] - 2.0 * dotv<D>(y, s_gL + zn * D);
           dl_z = -0.5 * wj * (lin_n - lin_p);
-          hp_stay = halfD * logw - 0.5 * wj * lin_p;   // per-spot part of plogLik if the label stays
-          hp_move = halfD * logw - 0.5 * wj * lin_n;   // ... if it moves (:1035, :1048)
+          hp_stay = -0.5 * wj * lin_p;   // per-spot part of plogLik if the label stays
+          hp_move = -0.5 * wj * lin_n;   // ... if it moves (:1035, :1048)
         }
         // ---- sequential label updates inside each parent: r = 0..S-1, neighbour labels live (:984,:1029-1051)
         for (int turn = 0; turn < S; turn++) {
@@ -263,11 +273,15 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         zs[tid] = (uint8_t) (active ? zfinal : 255);
       }
       __syncthreads();
-      tile_accumulate<D>(acc, a.SL, tile, sws, wvs, zs, true, false, tid);
+      tile_pairs_mma<D>(C, tile, warp, lane);
+      tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }
-    block_reduce2(hp_acc, nacc_y, red, tid);
-    if (tid == 0) { acc[a.SL.hp] = hp_acc; acc[a.SL.nacc] = nacc_y; }
+    double lws = lw.value();
+    block_reduce3(hp_acc, nacc_y, lws, red, tid);
+    if (tid == 0) { acc[a.SL.hp] = hp_acc + halfD * lws; acc[a.SL.nacc] = nacc_y; }
+    tile_pairs_fold<D>(C, ct, acc + a.SL.T, tid);
+    tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
     for (int e2 = tid; e2 < E; e2 += kBlock) out[e2] = acc[e2];

@@ -17,7 +17,7 @@ constexpr int kBlock = 128;       // threads per sweep CTA = spots per tile
 constexpr int kMaxD = 32;
 constexpr int kMaxDeg = 16;
 constexpr int kGroups = 64;       // fixed virtual shards of the deterministic two-level reduction
-constexpr int kTileLd = kBlock + 2;   // shared-memory tile row stride (16 B aligned, conflict free)
+constexpr int kTileLd = kBlock + 4;   // tile row stride = 4 (mod 16) doubles: DMMA fragment loads conflict free
 constexpr uint32_t BSB_COMPAT_Q1_BIT = 1u;
 constexpr uint32_t BSB_COMPAT_Q3_BIT = 4u;
 constexpr int BSB_DEVERR_NUMERIC = 1;   // NaN probability / Wishart df <= 0 / not positive definite

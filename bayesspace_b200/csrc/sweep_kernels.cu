@@ -14,6 +14,7 @@
 //  * shared precision: the quadratic form is expanded, q(y, mu_k) = y^T M y - 2 y^T (M mu_k)
 //    + mu_k^T M mu_k.  y^T M y cancels in the MH ratio; its sum over spots (needed only by the
 //    plogLik diagnostic, :305-307) is tr(M sum_j w_j y_j y_j^T), taken from the statistics;
+//  * sum_j log w_j (plogLik only) is accumulated as a product of mantissas, one log per segment;
 //  * Y is centred by its column means at upload (translation invariance), which keeps the
 //    expansion well conditioned.
 #include "kernels.hpp"
@@ -29,11 +30,12 @@ namespace {
 
 // Shared-memory carve-up of k_sweep (offsets in doubles).
 struct SweepSmem {
-  int g, c, gL, cL, PL, PM, logdet, tile, sws, wvs, acc, red, zs_bytes_off;
+  int g, c, gL, cL, PL, PM, logdet, tile, sws, wvs, acc, accP, ct, red, zs_bytes_off, P;
   size_t bytes;
 };
 __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int np, int E, bool tdist, bool vvv) {
   SweepSmem s;
+  const int DP = (D + 7) / 8 * 8, NT = DP / 8, NTILES = NT * (NT + 1) / 2;
   int o = 0;
   s.g = o; o += q * D;
   s.c = o; o += q;
@@ -43,11 +45,14 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int
   s.PM = o; o += vvv ? nl * np : 0;
   s.logdet = o; o += vvv ? nl : 0;
   o = (o + 1) & ~1;   // 16 B alignment of the tile
-  s.tile = o; o += D * kTileLd;
+  s.tile = o; o += DP * kTileLd;
   s.sws = o; o += kBlock;
   s.wvs = o; o += kBlock;
   s.acc = o; o += E;
-  s.red = o; o += 2 * (kBlock / 32);
+  s.P = cluster_sum_parts(D, q);
+  s.accP = o; o += s.P * q * (D + 2);
+  s.ct = o; o += (kBlock / 32) * NTILES * 64;
+  s.red = o; o += 3 * (kBlock / 32);
   s.zs_bytes_off = o * 8;
   s.bytes = (size_t) o * 8 + kBlock;
   return s;
@@ -56,44 +61,50 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int
 template <int D, bool TDIST, bool VVV>
 __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NP = D * (D + 1) / 2;
-  const int tid = threadIdx.x;
+  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = a.PL.q, nl = a.PL.nl, E = a.SL.E;
   const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV);
   double *s_g = sm + L.g, *s_c = sm + L.c, *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL;
   double *s_PM = sm + L.PM, *s_logdet = sm + L.logdet, *tile = sm + L.tile, *sws = sm + L.sws;
-  double *wvs = sm + L.wvs, *acc = sm + L.acc, *red = sm + L.red;
+  double *wvs = sm + L.wvs, *acc = sm + L.acc, *accP = sm + L.accP, *ct = sm + L.ct, *red = sm + L.red;
   uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
+  const int P = L.P;
 
   const bool stats_only = a.flags & SW_STATS_ONLY, dry = a.flags & SW_DRY;
   if (*a.err) return;
   if (!stats_only) {
-    const double *P = a.params;
-    for (int e = tid; e < q * D; e += kBlock) s_g[e] = P[a.PL.g + e];
-    for (int e = tid; e < q; e += kBlock) s_c[e] = P[a.PL.c + e];
+    const double *Pm = a.params;
+    for (int e = tid; e < q * D; e += kBlock) s_g[e] = Pm[a.PL.g + e];
+    for (int e = tid; e < q; e += kBlock) s_c[e] = Pm[a.PL.c + e];
     if (TDIST) {
-      for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
-      for (int e = tid; e < q; e += kBlock) s_cL[e] = P[a.PL.cL + e];
-      for (int e = tid; e < nl * NP; e += kBlock) s_PL[e] = P[a.PL.PL + e];
+      for (int e = tid; e < q * D; e += kBlock) s_gL[e] = Pm[a.PL.gL + e];
+      for (int e = tid; e < q; e += kBlock) s_cL[e] = Pm[a.PL.cL + e];
+      for (int e = tid; e < nl * NP; e += kBlock) s_PL[e] = Pm[a.PL.PL + e];
     }
     if (VVV) {
-      for (int e = tid; e < nl * NP; e += kBlock) s_PM[e] = P[a.PL.PM + e];
-      for (int e = tid; e < nl; e += kBlock) s_logdet[e] = P[a.PL.logdet + e];
+      for (int e = tid; e < nl * NP; e += kBlock) s_PM[e] = Pm[a.PL.PM + e];
+      for (int e = tid; e < nl; e += kBlock) s_logdet[e] = Pm[a.PL.logdet + e];
     }
   }
+  for (int e = tid; e < (DP - D) * kTileLd; e += kBlock) tile[D * kTileLd + e] = 0.0;   // padding rows of the tile
   const Key key{a.key0, a.key1};
   const uint32_t it = *a.iter + a.iter_add;
   const double w_alpha = (double) ((D + 4) / 2);   // quirk Q2: integer division (src/cluster.cpp:508)
   const double halfD = 0.5 * D;
   const bool do_pairs = !(a.flags & SW_NO_PAIRS) && a.SL.nlT > 0;
   const bool per_cluster_pairs = a.SL.nlT > 1;
-
   __syncthreads();
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
+    double C[NTILES][2];
+#pragma unroll
+    for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
     double hp_acc = 0.0, nacc = 0.0;
+    LogProd lw;
 
     for (int base = 0; base < count; base += kBlock) {
       const bool active = base + tid < count;
@@ -129,47 +140,45 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
             pot_p = a.gamma / deg * 2 * cp;
             pot_n = a.gamma / deg * 2 * cn;
           }
-          double logw = 0.0;
           if (TDIST) {
             // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518, :655-660)
             const double aL = quadform<D>(y, s_PL + (VVV ? zk * NP : 0));
             const double bL = dotv<D>(y, s_gL + zk * D);
             const double quad = aL - 2.0 * bL + s_cL[zk];
             wj = rng_gamma(key, P_SPOT_GAMMA, og, it, w_alpha, 2.0 / (quad + 4.0));
-            logw = log(wj);
           }
           const double lin_p = s_c[zk] - 2.0 * dotv<D>(y, s_g + zk * D);
           const double lin_n = s_c[zn] - 2.0 * dotv<D>(y, s_g + zn * D);
-          double delta, hp_part, hp_full = 0.0, hn_full = 0.0;
+          // the (d/2) log w_j term is common to both labels: it only enters plogLik (via lw)
+          double delta, hp_part, aP = 0.0, aN = 0.0, ldp = 0.0, ldn = 0.0;
           if (VVV) {
-            const double ap = quadform<D>(y, s_PM + zk * NP), an = quadform<D>(y, s_PM + zn * NP);
-            const double hp = pot_p + (s_logdet[zk] + halfD * logw - 0.5 * wj * (ap + lin_p));
-            const double hn = pot_n + (s_logdet[zn] + halfD * logw - 0.5 * wj * (an + lin_n));
+            aP = quadform<D>(y, s_PM + zk * NP);
+            aN = quadform<D>(y, s_PM + zn * NP);
+            ldp = s_logdet[zk];
+            ldn = s_logdet[zn];
+            const double hp = pot_p + (ldp - 0.5 * wj * (aP + lin_p));
+            const double hn = pot_n + (ldn - 0.5 * wj * (aN + lin_n));
             delta = hn - hp;
             hp_part = hp;
-            if (dry) {
-              hp_full = hp - halfD * 1.8378770664093454835606594728112;
-              hn_full = hn - halfD * 1.8378770664093454835606594728112;
-            }
           } else {
             delta = (pot_n - pot_p) - 0.5 * wj * (lin_n - lin_p);
-            hp_part = pot_p + halfD * logw - 0.5 * wj * lin_p;
-            if (dry) {
-              const double aM = quadform<D>(y, a.params + a.PL.PM);
-              const double cst = a.params[a.PL.logdet] - halfD * 1.8378770664093454835606594728112;
-              hp_full = pot_p + (cst + halfD * logw - 0.5 * wj * (aM + lin_p));
-              hn_full = pot_n + (cst + halfD * logw - 0.5 * wj * (aM + lin_n));
-            }
+            hp_part = pot_p - 0.5 * wj * lin_p;
           }
           double prob = exp(delta);
           if (prob > 1.0) prob = 1.0;
           if (prob != prob) atomicExch(a.err, BSB_DEVERR_NUMERIC);   // NA probability (Rcpp sample() stops)
           const bool accept = sample_two(prob, u_acc);
           if (dry) {
+            const double LOG2PI = 1.8378770664093454835606594728112;
+            const double logw = TDIST ? log(wj) : 0.0;
+            if (!VVV) {
+              aP = aN = quadform<D>(y, a.params + a.PL.PM);
+              ldp = ldn = a.params[a.PL.logdet];
+            }
             a.dry_znew[og] = zn + 1;
             a.dry_w[og] = wj;
-            a.dry_hp[og] = hp_full;
-            a.dry_hn[og] = hn_full;
+            a.dry_hp[og] = pot_p + ((ldp - halfD * LOG2PI) + halfD * logw - 0.5 * wj * (aP + lin_p));
+            a.dry_hn[og] = pot_n + ((ldn - halfD * LOG2PI) + halfD * logw - 0.5 * wj * (aN + lin_n));
             a.dry_prob[og] = prob;
             a.dry_acc[og] = accept ? 1 : 0;
           } else {
@@ -178,13 +187,16 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
               zfinal = zn;
               nacc += 1.0;
             }
-            if (TDIST) a.w[j] = wj;
+            if (TDIST) {
+              a.w[j] = wj;
+              lw.mul(wj);
+            }
             hp_acc += hp_part;
           }
         }
       }
       if (dry) continue;
-      // ---- stage sqrt(w) y, then every thread folds its statistic roles over the tile ----------
+      // ---- stage sqrt(w) y; fold the tile into the segment's statistics -------------------------
       {
         const double sw = active ? sqrt(wj) : 0.0;
 #pragma unroll
@@ -194,13 +206,23 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
         zs[tid] = (uint8_t) zfinal;
       }
       __syncthreads();
-      tile_accumulate<D>(acc, a.SL, tile, sws, wvs, zs, do_pairs, per_cluster_pairs, tid);
+      if (do_pairs) {
+        if (!per_cluster_pairs) tile_pairs_mma<D>(C, tile, warp, lane);
+        else tile_pairs_per_cluster<D>(acc + a.SL.T, tile, zs, tid);
+      }
+      tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }
     if (dry) continue;
-    // ---- block-reduce the scalar parts in a fixed order and publish the segment's record -------
-    block_reduce2(hp_acc, nacc, red, tid);
-    if (tid == 0) { acc[a.SL.hp] = hp_acc; acc[a.SL.nacc] = nacc; }
+    // ---- fold warps / parts in a fixed order and publish the segment's record --------------------
+    double lws = TDIST ? lw.value() : 0.0;
+    block_reduce3(hp_acc, nacc, lws, red, tid);
+    if (tid == 0) {
+      acc[a.SL.hp] = hp_acc + halfD * lws;
+      acc[a.SL.nacc] = nacc;
+    }
+    if (do_pairs && !per_cluster_pairs) tile_pairs_fold<D>(C, ct, acc + a.SL.T, tid);
+    tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
     for (int e = tid; e < E; e += kBlock) out[e] = acc[e];
@@ -233,15 +255,11 @@ int sweep_max_blocks(int tdist, int vvv, size_t smem) {
   int nb = 0;
   constexpr int D = BSB_D;
   if (tdist) {
-    if (vvv) { cudaFuncSetAttribute(k_sweep<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-               cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, true, true>, kBlock, smem); }
-    else { cudaFuncSetAttribute(k_sweep<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, true, false>, kBlock, smem); }
+    if (vvv) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, true, true>, kBlock, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, true, false>, kBlock, smem);
   } else {
-    if (vvv) { cudaFuncSetAttribute(k_sweep<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-               cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, false, true>, kBlock, smem); }
-    else { cudaFuncSetAttribute(k_sweep<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, false, false>, kBlock, smem); }
+    if (vvv) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, false, true>, kBlock, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sweep<D, false, false>, kBlock, smem);
   }
   return nb;
 }

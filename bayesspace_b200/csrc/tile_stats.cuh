@@ -1,10 +1,18 @@
 // tile_stats.cuh -- fused sufficient statistics of one tile of kBlock spots (device).
 //
-// After a CTA has updated a tile, every thread has staged sqrt(w_j) y_j, sqrt(w_j), w_j and the
-// final label of its spot in shared memory.  Each thread then owns a few "roles" -- one (a,b)
-// pair of sum w y y^T, one column of the per-cluster sums s_k, n_k or the counts -- and folds the
-// whole tile into its roles in spot order.  The order is fixed, so records are bit-reproducible.
-// Labels are piecewise constant along a tile (spatial domains), hence the run-length flushes.
+// After a CTA has updated a tile, every thread has staged u_j = sqrt(w_j) y_j (one shared-memory row
+// per PC, kTileLd doubles apart), sqrt(w_j), w_j and the final label of its spot.  Two reductions
+// then run over the tile, both in a fixed order so that records are bit-reproducible:
+//
+//  * pooled second moments  T = sum_j u_j u_j^T  (the only GEMM-shaped piece of the path: a
+//    d x 128 by 128 x d FP64 SYRK per tile).  It runs on the FP64 tensor pipe with
+//    mma.sync.m8n8k4.f64 (DMMA): each warp owns every 4th group of 4 spots, keeps the 8x8 output
+//    tiles of the upper triangle in registers across the whole segment, and the 4 warps are
+//    folded once per segment.  Measured on B200: DMMA sustains the full FP64 rate (37 TFLOP/s) at
+//    1/8 of the issue slots of DFMA, which is what matters here (the sweep is issue-bound).
+//  * per-cluster sums  s_k = sum w y, n_k = sum w, counts: thread (column c, part p) walks spots
+//    p, p+P, p+2P, ... of the tile with a run-length flush (labels are piecewise constant along a
+//    tile), into its private accumulator row; parts are folded once per segment.
 //
 // Replaces find(z == k) / sum(Yrows, 0) / (Y - mu)^T diag(w) (Y - mu) of the reference's mu and
 // lambda updates (src/cluster.cpp:249-253, :265, :482-486, :500, :884-887, :901), which re-read
@@ -14,6 +22,14 @@
 
 namespace bsb {
 
+template <int D>
+struct TileGeom {
+  static constexpr int NT = (D + 7) / 8;          // 8-row tiles of the (padded) PC dimension
+  static constexpr int DP = NT * 8;               // padded rows of the shared-memory tile
+  static constexpr int NTILES = NT * (NT + 1) / 2;   // upper-triangular 8x8 output tiles
+  static constexpr int NP = D * (D + 1) / 2;
+};
+
 __device__ __forceinline__ void pair_from_index(int p, int d, int &a, int &b) {
   a = 0;
   int rem = p, len = d;
@@ -21,79 +37,159 @@ __device__ __forceinline__ void pair_from_index(int p, int d, int &a, int &b) {
   b = a + rem;
 }
 
-// zs[t] == 255 marks an empty slot of the tile (its staged values are zero).
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// This warp's share of T += U U^T over one tile (U = DP x kBlock in shared memory).
+// A fragment: lane holds U[8i + (lane>>2)][t0 + (lane&3)]; the B fragment of row-tile j is the same
+// register as the A fragment of row-tile j, so NT loads feed NTILES DMMAs per group of 4 spots.
 template <int D>
-__device__ __forceinline__ void tile_accumulate(double *acc, const StatLayout &SL, const double *tile,
-                                                const double *sws, const double *wvs, const uint8_t *zs,
-                                                bool do_pairs, bool per_cluster_pairs, int tid) {
-  constexpr int NP = D * (D + 1) / 2;
-  for (int role = tid; role < NP + D + 2; role += kBlock) {
-    if (role < NP) {
-      if (!do_pairs) continue;
-      int pa, pb;
-      pair_from_index(role, D, pa, pb);
-      const double *ua = tile + pa * kTileLd, *ub = tile + pb * kTileLd;
-      if (!per_cluster_pairs) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-        for (int t = 0; t < kBlock; t += 2) {
-          const double2 va = *reinterpret_cast<const double2 *>(ua + t);
-          const double2 vb = *reinterpret_cast<const double2 *>(ub + t);
-          s0 = fma(va.x, vb.x, s0);
-          s1 = fma(va.y, vb.y, s1);
-        }
-        acc[SL.T + role] += s0 + s1;
-      } else {
-        int cur = 255;
-        double s = 0.0;
-        for (int t = 0; t < kBlock; t++) {
-          const int k = zs[t];
-          if (k == 255) continue;
-          if (k != cur) {
-            if (cur != 255) acc[SL.T + cur * NP + role] += s;
-            s = 0.0;
-            cur = k;
-          }
-          s = fma(ua[t], ub[t], s);
-        }
-        if (cur != 255) acc[SL.T + cur * NP + role] += s;
-      }
-    } else {
-      const int c = role - NP;   // c < D: column of s_k; c == D: n_k; c == D+1: counts
-      const int off = c < D ? SL.sk : (c == D ? SL.nk : SL.cnt);
-      const int stride = c < D ? D : 1, col = c < D ? c : 0;
-      int cur = 255;
-      double s = 0.0;
-      for (int t = 0; t < kBlock; t++) {
-        const int k = zs[t];
-        if (k == 255) continue;
-        if (k != cur) {
-          if (cur != 255) acc[off + cur * stride + col] += s;
-          s = 0.0;
-          cur = k;
-        }
-        s += c < D ? sws[t] * tile[c * kTileLd + t] : (c == D ? wvs[t] : 1.0);
-      }
-      if (cur != 255) acc[off + cur * stride + col] += s;
-    }
+__device__ __forceinline__ void tile_pairs_mma(double (&C)[TileGeom<D>::NTILES][2], const double *tile, int warp,
+                                               int lane) {
+  constexpr int NT = TileGeom<D>::NT, NW = kBlock / 32;
+  const double *base = tile + (lane >> 2) * kTileLd + (lane & 3);
+#pragma unroll
+  for (int s = 0; s < kBlock / 4 / NW; s++) {
+    const int t0 = (warp + s * NW) * 4;
+    double f[NT];
+#pragma unroll
+    for (int i = 0; i < NT; i++) f[i] = base[i * 8 * kTileLd + t0];
+    int tix = 0;
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+#pragma unroll
+      for (int j = i; j < NT; j++) dmma_m8n8k4(C[tix++], f[i], f[j]);
   }
 }
 
-// Fixed-order CTA reduction of two per-thread scalars; result valid on thread 0.
-__device__ __forceinline__ void block_reduce2(double &x, double &y, double *red, int tid) {
+// Segment end: fold the warps' output tiles (fixed order) into the record's T entries.
+// scratch: NW * NTILES * 64 doubles.  Contains a __syncthreads().
+template <int D>
+__device__ __forceinline__ void tile_pairs_fold(const double (&C)[TileGeom<D>::NTILES][2], double *scratch,
+                                                double *accT, int tid) {
+  constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, NP = TileGeom<D>::NP, NW = kBlock / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int t = 0; t < NTILES; t++) {
+    double *dst = scratch + ((size_t) warp * NTILES + t) * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
+    dst[0] = C[t][0];
+    dst[1] = C[t][1];
+  }
+  __syncthreads();
+  for (int p = tid; p < NP; p += kBlock) {
+    int a, b;
+    pair_from_index(p, D, a, b);
+    const int i = a >> 3, j = b >> 3;
+    const int t = i * NT - i * (i - 1) / 2 + (j - i);
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) s += scratch[((size_t) w * NTILES + t) * 64 + (a & 7) * 8 + (b & 7)];
+    accT[p] = s;
+  }
+}
+
+// Per-cluster second moments (VVV samplers): scalar run-length path, one (a,b) pair per thread.
+template <int D>
+__device__ __forceinline__ void tile_pairs_per_cluster(double *accT, const double *tile, const uint8_t *zs, int tid) {
+  constexpr int NP = TileGeom<D>::NP;
+  for (int role = tid; role < NP; role += kBlock) {
+    int pa, pb;
+    pair_from_index(role, D, pa, pb);
+    const double *ua = tile + pa * kTileLd, *ub = tile + pb * kTileLd;
+    int cur = 255;
+    double s = 0.0;
+    for (int t = 0; t < kBlock; t++) {
+      const int k = zs[t];
+      if (k == 255) continue;
+      if (k != cur) {
+        if (cur != 255) accT[cur * NP + role] += s;
+        s = 0.0;
+        cur = k;
+      }
+      s = fma(ua[t], ub[t], s);
+    }
+    if (cur != 255) accT[cur * NP + role] += s;
+  }
+}
+
+// Per-cluster sums.  Role (c, p): column c in [0, D+2) (D PCs, then w, then the count), part p in [0, P).
+// accP: P * q * (D+2) doubles, accP[(p*q + k)*(D+2) + c].  zs[t] == 255 marks an empty slot.
+template <int D>
+__device__ __forceinline__ void tile_cluster_sums(double *accP, int P, int q, const double *tile, const double *sws,
+                                                  const double *wvs, const uint8_t *zs, int tid) {
+  constexpr int NC = D + 2;
+  if (tid >= NC * P) return;
+  const int c = tid / P, p = tid - c * P;
+  double *mine = accP + (size_t) p * q * NC + c;
+  int cur = 255;
+  double s = 0.0;
+  for (int t = p; t < kBlock; t += P) {
+    const int k = zs[t];
+    if (k == 255) continue;
+    if (k != cur) {
+      if (cur != 255) mine[cur * NC] += s;
+      s = 0.0;
+      cur = k;
+    }
+    s += c < D ? sws[t] * tile[c * kTileLd + t] : (c == D ? wvs[t] : 1.0);
+  }
+  if (cur != 255) mine[cur * NC] += s;
+}
+
+// Segment end: fold the P parts (fixed order) into the record's s_k / n_k / count entries.
+template <int D>
+__device__ __forceinline__ void tile_cluster_fold(const double *accP, int P, int q, double *acc, const StatLayout &SL,
+                                                  int tid) {
+  constexpr int NC = D + 2;
+  for (int e = tid; e < q * NC; e += kBlock) {
+    const int k = e / NC, c = e - k * NC;
+    double s = 0.0;
+    for (int p = 0; p < P; p++) s += accP[((size_t) p * q + k) * NC + c];
+    if (c < D) acc[SL.sk + k * D + c] = s;
+    else if (c == D) acc[SL.nk + k] = s;
+    else acc[SL.cnt + k] = s;
+  }
+}
+
+// Number of parts of tile_cluster_sums: as many as fit the CTA and a 48 KB accumulator budget.
+__host__ __device__ inline int cluster_sum_parts(int D, int q) {
+  int P = kBlock / (D + 2);
+  const int cap = (48 * 1024) / (q * (D + 2) * 8);
+  if (P > cap) P = cap;
+  return P < 1 ? 1 : P;
+}
+
+// Fixed-order CTA reduction of three per-thread scalars; results valid on thread 0.  red: 3 * warps doubles.
+__device__ __forceinline__ void block_reduce3(double &x, double &y, double &z, double *red, int tid) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     x += __shfl_xor_sync(0xffffffffu, x, o);
     y += __shfl_xor_sync(0xffffffffu, y, o);
+    z += __shfl_xor_sync(0xffffffffu, z, o);
   }
-  if ((tid & 31) == 0) { red[2 * (tid >> 5)] = x; red[2 * (tid >> 5) + 1] = y; }
+  if ((tid & 31) == 0) { red[3 * (tid >> 5)] = x; red[3 * (tid >> 5) + 1] = y; red[3 * (tid >> 5) + 2] = z; }
   __syncthreads();
   if (tid == 0) {
-    double h = 0.0, na = 0.0;
-    for (int wv = 0; wv < kBlock / 32; wv++) { h += red[2 * wv]; na += red[2 * wv + 1]; }
-    x = h; y = na;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int wv = 0; wv < kBlock / 32; wv++) { a += red[3 * wv]; b += red[3 * wv + 1]; c += red[3 * wv + 2]; }
+    x = a; y = b; z = c;
   }
 }
+
+// sum_j log w_j without one log per spot: running product of mantissas + integer exponents.
+struct LogProd {
+  double m = 1.0;
+  int e = 0;
+  __device__ __forceinline__ void mul(double w) {
+    int ex;
+    m *= frexp(w, &ex);
+    e += ex;
+    if (m < 1e-280) { m = frexp(m, &ex); e += ex; }
+  }
+  __device__ __forceinline__ double value() const { return log(m) + (double) e * 0.69314718055994530942; }
+};
 
 template <int D>
 __device__ __forceinline__ double quadform(const double (&y)[D], const double *__restrict__ P) {
