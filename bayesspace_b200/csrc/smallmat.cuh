@@ -34,6 +34,53 @@ __device__ inline bool warp_chol_upper(const double *A, double *R, int d, int la
   return ok;
 }
 
+// U (upper, U U^T = A) from the upper triangle of A: the Cholesky factorisation taken from the last
+// row / column backwards.  If A = X^-1 with X = R^T R (R upper), then U = R^-1: this is how the kernels
+// obtain chol(X^-1) and inv(chol(Sigma)) without forming an inverse.  A and U must not alias.
+__device__ inline bool warp_revchol_upper(const double *A, double *U, int d, int lane) {
+  // right-looking, in place on a copy: after column j is scaled, the leading (j x j) block is
+  // down-dated by the outer product of that column -- independent FMAs, no long dependent chain.
+  for (int e = lane; e < d * d; e += 32) U[e] = (e % d) <= (e / d) ? A[e] : 0.0;
+  __syncwarp();
+  bool ok = true;
+  for (int j = d - 1; j >= 0; j--) {
+    const double s = SM_AT(U, j, j);
+    if (!(s > 0.0)) ok = false;
+    const double ujj = sqrt(s), inv = 1.0 / ujj;
+    __syncwarp();
+    for (int i = lane; i < j; i += 32) SM_AT(U, i, j) *= inv;
+    if (lane == 0) SM_AT(U, j, j) = ujj;
+    __syncwarp();
+    for (int k = lane; k < j; k += 32) {
+      const double ukj = SM_AT(U, k, j);
+#pragma unroll 4
+      for (int i = 0; i <= k; i++) SM_AT(U, i, k) -= SM_AT(U, i, j) * ukj;
+    }
+    __syncwarp();
+  }
+  return ok;
+}
+
+// y = R x for upper-triangular R (y_i = sum_{j>=i} R_ij x_j); x, y in shared memory, not aliased.
+__device__ inline void warp_triu_matvec(const double *R, const double *x, double *y, int d, int lane) {
+  for (int i = lane; i < d; i += 32) {
+    double s = 0.0;
+    for (int j = i; j < d; j++) s += SM_AT(R, i, j) * x[j];
+    y[i] = s;
+  }
+  __syncwarp();
+}
+
+// y = R^T x for upper-triangular R (y_j = sum_{i<=j} R_ij x_i).
+__device__ inline void warp_triu_matvec_t(const double *R, const double *x, double *y, int d, int lane) {
+  for (int j = lane; j < d; j += 32) {
+    double s = 0.0;
+    for (int i = 0; i <= j; i++) s += SM_AT(R, i, j) * x[i];
+    y[j] = s;
+  }
+  __syncwarp();
+}
+
 // T = R^-1 for upper-triangular R (T upper).  Must not alias.
 __device__ inline void warp_inv_upper(const double *R, double *T, int d, int lane) {
   for (int j = lane; j < d; j += 32) {
