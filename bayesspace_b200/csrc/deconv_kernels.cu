@@ -29,19 +29,19 @@ struct DeconvSmem {
 };
 __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, int E) {
   DeconvSmem s;
-  const int DP = (D + 7) / 8 * 8, NT = DP / 8, NTILES = NT * (NT + 1) / 2;
+  const int DP = (D + 1 + 7) / 8 * 8, NT = DP / 8, NFRAG = NT * (NT + 1) / 2 + 2 * NT;
   int o = 0;
   s.gL = o; o += q * D;
   s.cL = o; o += q;
   s.PL = o; o += np;
   o = (o + 1) & ~1;
-  s.tile = o; o += DP * kTileLd;
-  s.sws = o; o += kBlock;
+  const int tile_doubles = DP * kTileLd, fold_doubles = (kBlock / 32) * NFRAG * 64;   // fold scratch aliases the tile
+  s.tile = o; s.ct = o; o += tile_doubles > fold_doubles ? tile_doubles : fold_doubles;
+  s.sws = s.tile + D * kTileLd;   // sqrt(w) is row D of the tile
   s.wvs = o; o += kBlock;
   s.acc = o; o += E;
-  s.P = cluster_sum_parts(D, q);
+  s.P = q > 16 ? cluster_sum_parts(D, q) : 0;
   s.accP = o; o += s.P * q * (D + 2);
-  s.ct = o; o += (kBlock / 32) * NTILES * 64;
   s.red = o; o += 3 * (kBlock / 32);
   s.zs_bytes_off = o * 8;
   s.bytes = (size_t) o * 8 + kBlock;
@@ -51,7 +51,7 @@ __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, i
 template <int D, bool ADAPT>
 __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES;
+  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES, NT = TileGeom<D>::NT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = a.PL.q, E = a.SL.E, S = a.S;
   const DeconvSmem L = deconv_smem_layout(D, q, NP, E);
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
   const int P = L.P;
   if (*a.err) return;
-  for (int e = tid; e < (DP - D) * kTileLd; e += kBlock) tile[D * kTileLd + e] = 0.0;   // padding rows of the tile
+  const bool scalar_sums = q > 16;
+  const int nh = scalar_sums ? 0 : (q + 7) / 8;
   if (!a.stats_only) {
     const double *P = a.params;
     for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
@@ -82,9 +83,12 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
-    double C[NTILES][2];
+    for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
+    double C[NTILES][2], CH[NT][2][2];
 #pragma unroll
     for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; t++) CH[t][0][0] = CH[t][0][1] = CH[t][1][0] = CH[t][1][1] = 0.0;
     double hp_acc = 0.0, nacc_y = 0.0;
     LogProd lw;
 
@@ -273,15 +277,15 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         zs[tid] = (uint8_t) (active ? zfinal : 255);
       }
       __syncthreads();
-      tile_pairs_mma<D>(C, tile, warp, lane);
-      tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
+      tile_stats_mma<D>(C, CH, tile, zs, true, nh, warp, lane);
+      if (scalar_sums) tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }
     double lws = lw.value();
     block_reduce3(hp_acc, nacc_y, lws, red, tid);
     if (tid == 0) { acc[a.SL.hp] = hp_acc + halfD * lws; acc[a.SL.nacc] = nacc_y; }
-    tile_pairs_fold<D>(C, ct, acc + a.SL.T, tid);
-    tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
+    tile_stats_fold<D>(C, CH, ct, acc, a.SL, true, nh ? q : 0, tid);
+    if (scalar_sums) tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
     for (int e2 = tid; e2 < E; e2 += kBlock) out[e2] = acc[e2];

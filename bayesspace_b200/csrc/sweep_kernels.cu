@@ -33,9 +33,10 @@ struct SweepSmem {
   int g, c, gL, cL, PL, PM, logdet, tile, sws, wvs, acc, accP, ct, red, zs_bytes_off, P;
   size_t bytes;
 };
-__host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int np, int E, bool tdist, bool vvv) {
+__host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int np, int E, bool tdist, bool vvv,
+                                                       bool vvv_pairs) {
   SweepSmem s;
-  const int DP = (D + 7) / 8 * 8, NT = DP / 8, NTILES = NT * (NT + 1) / 2;
+  const int DP = (D + 1 + 7) / 8 * 8, NT = DP / 8, NFRAG = NT * (NT + 1) / 2 + 2 * NT;
   int o = 0;
   s.g = o; o += q * D;
   s.c = o; o += q;
@@ -45,13 +46,14 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int
   s.PM = o; o += vvv ? nl * np : 0;
   s.logdet = o; o += vvv ? nl : 0;
   o = (o + 1) & ~1;   // 16 B alignment of the tile
-  s.tile = o; o += DP * kTileLd;
-  s.sws = o; o += kBlock;
+  const int tile_doubles = DP * kTileLd, fold_doubles = (kBlock / 32) * NFRAG * 64;   // fold scratch aliases the tile
+  s.tile = o; s.ct = o; o += tile_doubles > fold_doubles ? tile_doubles : fold_doubles;
+  s.sws = s.tile + D * kTileLd;   // sqrt(w) is row D of the tile
   s.wvs = o; o += kBlock;
   s.acc = o; o += E;
-  s.P = cluster_sum_parts(D, q);
+  const bool scalar_sums = vvv_pairs || q > 16;
+  s.P = scalar_sums ? cluster_sum_parts(D, q) : 0;
   s.accP = o; o += s.P * q * (D + 2);
-  s.ct = o; o += (kBlock / 32) * NTILES * 64;
   s.red = o; o += 3 * (kBlock / 32);
   s.zs_bytes_off = o * 8;
   s.bytes = (size_t) o * 8 + kBlock;
@@ -61,10 +63,10 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int
 template <int D, bool TDIST, bool VVV>
 __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES;
+  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES, NT = TileGeom<D>::NT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = a.PL.q, nl = a.PL.nl, E = a.SL.E;
-  const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV);
+  const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV, a.SL.nlT > 1);
   double *s_g = sm + L.g, *s_c = sm + L.c, *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL;
   double *s_PM = sm + L.PM, *s_logdet = sm + L.logdet, *tile = sm + L.tile, *sws = sm + L.sws;
   double *wvs = sm + L.wvs, *acc = sm + L.acc, *accP = sm + L.accP, *ct = sm + L.ct, *red = sm + L.red;
@@ -87,22 +89,26 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
       for (int e = tid; e < nl; e += kBlock) s_logdet[e] = Pm[a.PL.logdet + e];
     }
   }
-  for (int e = tid; e < (DP - D) * kTileLd; e += kBlock) tile[D * kTileLd + e] = 0.0;   // padding rows of the tile
   const Key key{a.key0, a.key1};
   const uint32_t it = *a.iter + a.iter_add;
   const double w_alpha = (double) ((D + 4) / 2);   // quirk Q2: integer division (src/cluster.cpp:508)
   const double halfD = 0.5 * D;
   const bool do_pairs = !(a.flags & SW_NO_PAIRS) && a.SL.nlT > 0;
   const bool per_cluster_pairs = a.SL.nlT > 1;
+  const bool scalar_sums = per_cluster_pairs || q > 16;   // VVV samplers / many clusters: scalar reductions
+  const int nh = scalar_sums ? 0 : (q + 7) / 8;
   __syncthreads();
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
-    double C[NTILES][2];
+    for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
+    double C[NTILES][2], CH[NT][2][2];
 #pragma unroll
     for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; t++) CH[t][0][0] = CH[t][0][1] = CH[t][1][0] = CH[t][1][1] = 0.0;
     double hp_acc = 0.0, nacc = 0.0;
     LogProd lw;
 
@@ -206,11 +212,9 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
         zs[tid] = (uint8_t) zfinal;
       }
       __syncthreads();
-      if (do_pairs) {
-        if (!per_cluster_pairs) tile_pairs_mma<D>(C, tile, warp, lane);
-        else tile_pairs_per_cluster<D>(acc + a.SL.T, tile, zs, tid);
-      }
-      tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
+      if (do_pairs && per_cluster_pairs) tile_pairs_per_cluster<D>(acc + a.SL.T, tile, zs, tid);
+      if (!per_cluster_pairs && (do_pairs || nh)) tile_stats_mma<D>(C, CH, tile, zs, do_pairs, nh, warp, lane);
+      if (scalar_sums) tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }
     if (dry) continue;
@@ -221,8 +225,8 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
       acc[a.SL.hp] = hp_acc + halfD * lws;
       acc[a.SL.nacc] = nacc;
     }
-    if (do_pairs && !per_cluster_pairs) tile_pairs_fold<D>(C, ct, acc + a.SL.T, tid);
-    tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
+    if (!per_cluster_pairs) tile_stats_fold<D>(C, CH, ct, acc, a.SL, do_pairs, nh ? q : 0, tid);
+    if (scalar_sums) tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
     for (int e = tid; e < E; e += kBlock) out[e] = acc[e];
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
 template <bool TDIST, bool VVV>
 void launch_sweep_t(const SweepArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
-  const SweepSmem L = sweep_smem_layout(D, a.PL.q, a.PL.nl, D * (D + 1) / 2, a.SL.E, TDIST, VVV);
+  const SweepSmem L = sweep_smem_layout(D, a.PL.q, a.PL.nl, D * (D + 1) / 2, a.SL.E, TDIST, VVV, a.SL.nlT > 1);
   static size_t attr = 0;
   if (L.bytes > attr) {
     cudaFuncSetAttribute(k_sweep<D, TDIST, VVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.bytes);
@@ -248,7 +252,7 @@ void launch_sweep(int tdist, int vvv, const SweepArgs &a, int grid, cudaStream_t
 }
 
 size_t sweep_smem(int tdist, int vvv, const SweepArgs &a) {
-  return sweep_smem_layout(BSB_D, a.PL.q, a.PL.nl, BSB_D * (BSB_D + 1) / 2, a.SL.E, tdist, vvv).bytes;
+  return sweep_smem_layout(BSB_D, a.PL.q, a.PL.nl, BSB_D * (BSB_D + 1) / 2, a.SL.E, tdist, vvv, a.SL.nlT > 1).bytes;
 }
 
 int sweep_max_blocks(int tdist, int vvv, size_t smem) {

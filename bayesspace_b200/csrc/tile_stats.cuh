@@ -24,8 +24,9 @@ namespace bsb {
 
 template <int D>
 struct TileGeom {
-  static constexpr int NT = (D + 7) / 8;          // 8-row tiles of the (padded) PC dimension
+  static constexpr int NT = (D + 1 + 7) / 8;      // 8-row tiles of the staged rows: d PCs, then sqrt(w)
   static constexpr int DP = NT * 8;               // padded rows of the shared-memory tile
+  static constexpr int NFRAG = NT * (NT + 1) / 2 + 2 * NT;   // output tiles per warp incl. 2 label tiles per row tile
   static constexpr int NTILES = NT * (NT + 1) / 2;   // upper-triangular 8x8 output tiles
   static constexpr int NP = D * (D + 1) / 2;
 };
@@ -42,51 +43,85 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// This warp's share of T += U U^T over one tile (U = DP x kBlock in shared memory).
+// This warp's share of one tile, everything on the FP64 tensor pipe:
+//   C  += U U^T          (U = staged rows: sqrt(w) y_1..d, then sqrt(w); upper 8x8 tiles)  -> T
+//   CH += U H^T          (H_k[t] = sqrt(w_t) [z_t = k], built on the fly, k < 8*nh <= 16) -> s_k (rows < d), n_k (row d)
 // A fragment: lane holds U[8i + (lane>>2)][t0 + (lane&3)]; the B fragment of row-tile j is the same
-// register as the A fragment of row-tile j, so NT loads feed NTILES DMMAs per group of 4 spots.
+// register as the A fragment of row-tile j, so NT loads feed all the DMMAs of a group of 4 spots.
 template <int D>
-__device__ __forceinline__ void tile_pairs_mma(double (&C)[TileGeom<D>::NTILES][2], const double *tile, int warp,
+__device__ __forceinline__ void tile_stats_mma(double (&C)[TileGeom<D>::NTILES][2], double (&CH)[TileGeom<D>::NT][2][2],
+                                               const double *tile, const uint8_t *zs, bool do_pairs, int nh, int warp,
                                                int lane) {
   constexpr int NT = TileGeom<D>::NT, NW = kBlock / 32;
   const double *base = tile + (lane >> 2) * kTileLd + (lane & 3);
+  const double *swrow = tile + D * kTileLd + (lane & 3);
+  const int kc = lane >> 2;
 #pragma unroll
   for (int s = 0; s < kBlock / 4 / NW; s++) {
     const int t0 = (warp + s * NW) * 4;
     double f[NT];
 #pragma unroll
     for (int i = 0; i < NT; i++) f[i] = base[i * 8 * kTileLd + t0];
-    int tix = 0;
+    if (do_pairs) {
+      int tix = 0;
 #pragma unroll
-    for (int i = 0; i < NT; i++)
+      for (int i = 0; i < NT; i++)
 #pragma unroll
-      for (int j = i; j < NT; j++) dmma_m8n8k4(C[tix++], f[i], f[j]);
+        for (int j = i; j < NT; j++) dmma_m8n8k4(C[tix++], f[i], f[j]);
+    }
+    const int zt = zs[t0 + (lane & 3)];
+    const double swt = swrow[t0];
+    const double h0 = zt == kc ? swt : 0.0;
+#pragma unroll
+    for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][0], f[i], h0);
+    if (nh > 1) {
+      const double h1 = zt == kc + 8 ? swt : 0.0;
+#pragma unroll
+      for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][1], f[i], h1);
+    }
   }
 }
 
-// Segment end: fold the warps' output tiles (fixed order) into the record's T entries.
-// scratch: NW * NTILES * 64 doubles.  Contains a __syncthreads().
+// Segment end: fold the warps' output tiles (fixed order) into the record.  scratch: NW * NFRAG * 64 doubles
+// (may alias the tile).  Contains two __syncthreads().
 template <int D>
-__device__ __forceinline__ void tile_pairs_fold(const double (&C)[TileGeom<D>::NTILES][2], double *scratch,
-                                                double *accT, int tid) {
+__device__ __forceinline__ void tile_stats_fold(const double (&C)[TileGeom<D>::NTILES][2],
+                                                const double (&CH)[TileGeom<D>::NT][2][2], double *scratch, double *acc,
+                                                const StatLayout &SL, bool do_pairs, int q, int tid) {
   constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, NP = TileGeom<D>::NP, NW = kBlock / 32;
+  constexpr int NFRAG = TileGeom<D>::NFRAG;
   const int warp = tid >> 5, lane = tid & 31;
+  __syncthreads();   // the tile may be aliased by scratch
+  double *mine = scratch + (size_t) warp * NFRAG * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
 #pragma unroll
-  for (int t = 0; t < NTILES; t++) {
-    double *dst = scratch + ((size_t) warp * NTILES + t) * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
-    dst[0] = C[t][0];
-    dst[1] = C[t][1];
-  }
+  for (int t = 0; t < NTILES; t++) { mine[t * 64] = C[t][0]; mine[t * 64 + 1] = C[t][1]; }
+#pragma unroll
+  for (int i = 0; i < NT; i++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      mine[(NTILES + 2 * i + h) * 64] = CH[i][h][0];
+      mine[(NTILES + 2 * i + h) * 64 + 1] = CH[i][h][1];
+    }
   __syncthreads();
-  for (int p = tid; p < NP; p += kBlock) {
-    int a, b;
-    pair_from_index(p, D, a, b);
-    const int i = a >> 3, j = b >> 3;
-    const int t = i * NT - i * (i - 1) / 2 + (j - i);
+  if (do_pairs)
+    for (int p = tid; p < NP; p += kBlock) {
+      int a, b;
+      pair_from_index(p, D, a, b);
+      const int i = a >> 3, j = b >> 3;
+      const int t = i * NT - i * (i - 1) / 2 + (j - i);
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) s += scratch[((size_t) w * NFRAG + t) * 64 + (a & 7) * 8 + (b & 7)];
+      acc[SL.T + p] = s;
+    }
+  for (int e = tid; e < q * (D + 1); e += kBlock) {   // (cluster k, row a): a < D -> s_k[a], a == D -> n_k
+    const int k = e / (D + 1), a = e - k * (D + 1);
+    const int t = NTILES + 2 * (a >> 3) + (k >> 3);
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; w++) s += scratch[((size_t) w * NTILES + t) * 64 + (a & 7) * 8 + (b & 7)];
-    accT[p] = s;
+    for (int w = 0; w < NW; w++) s += scratch[((size_t) w * NFRAG + t) * 64 + (a & 7) * 8 + (k & 7)];
+    if (a < D) acc[SL.sk + k * D + a] = s;
+    else acc[SL.nk + k] = s;
   }
 }
 
