@@ -29,14 +29,14 @@ struct DeconvSmem {
 };
 __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, int E) {
   DeconvSmem s;
-  const int DP = (D + 1 + 7) / 8 * 8, NT = DP / 8, NFRAG = NT * (NT + 1) / 2 + 2 * NT;
+  const int DP = (D + 1 + 7) / 8 * 8, NFRAG = stats_frags(D, q > 16 ? 0 : (q + 7) / 8);
   int o = 0;
   s.gL = o; o += q * D;
   s.cL = o; o += q;
   s.PL = o; o += np;
   o = (o + 1) & ~1;
-  const int tile_doubles = DP * kTileLd, fold_doubles = (kBlock / 32) * NFRAG * 64;   // fold scratch aliases the tile
-  s.tile = o; s.ct = o; o += tile_doubles > fold_doubles ? tile_doubles : fold_doubles;
+  s.tile = o; o += DP * kTileLd;
+  s.ct = o; o += (kBlock / 32) * NFRAG * 64;   // DMMA output tiles, warp-private, resident across the segment
   s.sws = s.tile + D * kTileLd;   // sqrt(w) is row D of the tile
   s.wvs = o; o += kBlock;
   s.acc = o; o += E;
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   if (*a.err) return;
   const bool scalar_sums = q > 16;
   const int nh = scalar_sums ? 0 : (q + 7) / 8;
+  for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
   if (!a.stats_only) {
     const double *P = a.params;
     for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
@@ -83,12 +84,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
-    for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
-    double C[NTILES][2], CH[NT][2][2];
-#pragma unroll
-    for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
-#pragma unroll
-    for (int t = 0; t < NT; t++) CH[t][0][0] = CH[t][0][1] = CH[t][1][0] = CH[t][1][1] = 0.0;
+    for (int e = tid; e < (kBlock / 32) * stats_frags(D, nh) * 64; e += kBlock) ct[e] = 0.0;
     double hp_acc = 0.0, nacc_y = 0.0;
     LogProd lw;
 
@@ -277,14 +273,14 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         zs[tid] = (uint8_t) (active ? zfinal : 255);
       }
       __syncthreads();
-      tile_stats_mma<D>(C, CH, tile, zs, true, nh, warp, lane);
+      tile_stats_mma<D>(ct, tile, zs, true, nh, warp, lane);
       if (scalar_sums) tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }
     double lws = lw.value();
     block_reduce3(hp_acc, nacc_y, lws, red, tid);
     if (tid == 0) { acc[a.SL.hp] = hp_acc + halfD * lws; acc[a.SL.nacc] = nacc_y; }
-    tile_stats_fold<D>(C, CH, ct, acc, a.SL, true, nh ? q : 0, tid);
+    tile_stats_fold<D>(ct, acc, a.SL, true, nh ? q : 0, nh, tid);
     if (scalar_sums) tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;

@@ -30,13 +30,13 @@ namespace {
 
 // Shared-memory carve-up of k_sweep (offsets in doubles).
 struct SweepSmem {
-  int g, c, gL, cL, PL, PM, logdet, tile, sws, wvs, acc, accP, ct, red, zs_bytes_off, P;
+  int g, c, gL, cL, PL, PM, logdet, tile, sws, wvs, acc, accP, ct, red, ybuf, ellbuf, origbuf, zs_bytes_off, P;
   size_t bytes;
 };
 __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int np, int E, bool tdist, bool vvv,
-                                                       bool vvv_pairs) {
+                                                       bool vvv_pairs, int maxdeg) {
   SweepSmem s;
-  const int DP = (D + 1 + 7) / 8 * 8, NT = DP / 8, NFRAG = NT * (NT + 1) / 2 + 2 * NT;
+  const int DP = (D + 1 + 7) / 8 * 8, NFRAG = stats_frags(D, q > 16 ? 0 : (q + 7) / 8);
   int o = 0;
   s.g = o; o += q * D;
   s.c = o; o += q;
@@ -46,15 +46,18 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int
   s.PM = o; o += vvv ? nl * np : 0;
   s.logdet = o; o += vvv ? nl : 0;
   o = (o + 1) & ~1;   // 16 B alignment of the tile
-  const int tile_doubles = DP * kTileLd, fold_doubles = (kBlock / 32) * NFRAG * 64;   // fold scratch aliases the tile
-  s.tile = o; s.ct = o; o += tile_doubles > fold_doubles ? tile_doubles : fold_doubles;
-  s.sws = s.tile + D * kTileLd;   // sqrt(w) is row D of the tile
+  s.tile = o; o += 2 * DP * kTileLd;   // two buffers: cp.async landing zone of y, restaged in place as sqrt(w) y
+  s.ct = o; o += (kBlock / 32) * NFRAG * 64;   // DMMA output tiles, warp-private, resident across the segment
+  s.sws = 0;
   s.wvs = o; o += kBlock;
   s.acc = o; o += E;
   const bool scalar_sums = vvv_pairs || q > 16;
   s.P = scalar_sums ? cluster_sum_parts(D, q) : 0;
   s.accP = o; o += s.P * q * (D + 2);
   s.red = o; o += 3 * (kBlock / 32);
+  s.ybuf = s.tile;
+  s.ellbuf = o; o += (2 * maxdeg * kBlock + 1) / 2;       // neighbour ids (int32),
+  s.origbuf = o; o += kBlock;                             // original spot ids (int32, 2 buffers)
   s.zs_bytes_off = o * 8;
   s.bytes = (size_t) o * 8 + kBlock;
   return s;
@@ -66,12 +69,13 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
   constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES, NT = TileGeom<D>::NT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = a.PL.q, nl = a.PL.nl, E = a.SL.E;
-  const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV, a.SL.nlT > 1);
+  const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV, a.SL.nlT > 1, a.maxdeg);
   double *s_g = sm + L.g, *s_c = sm + L.c, *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL;
-  double *s_PM = sm + L.PM, *s_logdet = sm + L.logdet, *tile = sm + L.tile, *sws = sm + L.sws;
+  double *s_PM = sm + L.PM, *s_logdet = sm + L.logdet, *tile0 = sm + L.tile;
   double *wvs = sm + L.wvs, *acc = sm + L.acc, *accP = sm + L.accP, *ct = sm + L.ct, *red = sm + L.red;
   uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
   const int P = L.P;
+  int32_t *ellbuf = reinterpret_cast<int32_t *>(sm + L.ellbuf), *origbuf = reinterpret_cast<int32_t *>(sm + L.origbuf);
 
   const bool stats_only = a.flags & SW_STATS_ONLY, dry = a.flags & SW_DRY;
   if (*a.err) return;
@@ -89,6 +93,8 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
       for (int e = tid; e < nl; e += kBlock) s_logdet[e] = Pm[a.PL.logdet + e];
     }
   }
+  for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock)   // padding rows of both buffers
+    tile0[(D + 1) * kTileLd + e] = tile0[(DP + D + 1) * kTileLd + e] = 0.0;
   const Key key{a.key0, a.key1};
   const uint32_t it = *a.iter + a.iter_add;
   const double w_alpha = (double) ((D + 4) / 2);   // quirk Q2: integer division (src/cluster.cpp:508)
@@ -103,36 +109,53 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
-    for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
-    double C[NTILES][2], CH[NT][2][2];
-#pragma unroll
-    for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
-#pragma unroll
-    for (int t = 0; t < NT; t++) CH[t][0][0] = CH[t][0][1] = CH[t][1][0] = CH[t][1][1] = 0.0;
+    for (int e = tid; e < (kBlock / 32) * stats_frags(D, nh) * 64; e += kBlock) ct[e] = 0.0;
     double hp_acc = 0.0, nacc = 0.0;
     LogProd lw;
+    // Each thread streams the inputs of ITS spot of the next tile into shared memory with cp.async while
+    // the current tile is being processed (it is the only reader of what it copied: no barrier needed).
+    auto prefetch = [&](int buf, int pbase) {
+      if (pbase + tid < count) {
+        const int64_t pj = (int64_t) begin + pbase + tid;
+        const double *src = a.Y + pj;
+        double *dst = tile0 + buf * DP * kTileLd + tid;
+#pragma unroll 1
+        for (int c = 0; c < D; c++, src += a.ld, dst += kTileLd) cp_async8(dst, src);   // rolled: no hoisted addresses
+        const int32_t *esrc = a.ell + pj;
+        int32_t *edst = ellbuf + buf * a.maxdeg * kBlock + tid;
+#pragma unroll 1
+        for (int e = 0; e < a.maxdeg; e++, esrc += a.ld, edst += kBlock) cp_async4(edst, esrc);
+        cp_async4(origbuf + buf * kBlock + tid, a.orig + pj);
+      }
+      cp_async_commit();
+    };
+    prefetch(0, 0);
 
-    for (int base = 0; base < count; base += kBlock) {
+    for (int base = 0, tix = 0; base < count; base += kBlock, tix++) {
+      const int cur = tix & 1;
+      double *tile = tile0 + cur * DP * kTileLd, *sws = tile + D * kTileLd;
       const bool active = base + tid < count;
       const int64_t j = (int64_t) begin + base + tid;
+      if (base + kBlock < count) { prefetch(cur ^ 1, base + kBlock); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
       double y[D];
       double wj = 1.0;
       int zfinal = 255;
       if (active) {
 #pragma unroll
-        for (int c = 0; c < D; c++) y[c] = a.Y[(size_t) c * a.ld + j];
+        for (int c = 0; c < D; c++) y[c] = tile[c * kTileLd + tid];
         const int zk = a.z[j];
         zfinal = zk;
         if (stats_only) {
           if (TDIST) wj = a.w[j];
         } else {
-          const uint32_t og = (uint32_t) a.orig[j];
+          const uint32_t og = (uint32_t) origbuf[cur * kBlock + tid];
           double u_prop, u_acc;
           rng_uniform2(key, P_SPOT_U, og, it, 0u, u_prop, u_acc);
           const int zn = propose_label(zk, q, u_prop);
           int deg = 0, cp = 0, cn = 0;
           for (int e = 0; e < a.maxdeg; e++) {
-            const int32_t nb = a.ell[(size_t) e * a.ld + j];
+            const int32_t nb = ellbuf[(cur * a.maxdeg + e) * kBlock + tid];
             if (nb >= 0) {
               deg++;
               const int zu = a.z[nb];
@@ -213,7 +236,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
       }
       __syncthreads();
       if (do_pairs && per_cluster_pairs) tile_pairs_per_cluster<D>(acc + a.SL.T, tile, zs, tid);
-      if (!per_cluster_pairs && (do_pairs || nh)) tile_stats_mma<D>(C, CH, tile, zs, do_pairs, nh, warp, lane);
+      if (!per_cluster_pairs && (do_pairs || nh)) tile_stats_mma<D>(ct, tile, zs, do_pairs, nh, warp, lane);
       if (scalar_sums) tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
       acc[a.SL.hp] = hp_acc + halfD * lws;
       acc[a.SL.nacc] = nacc;
     }
-    if (!per_cluster_pairs) tile_stats_fold<D>(C, CH, ct, acc, a.SL, do_pairs, nh ? q : 0, tid);
+    if (!per_cluster_pairs) tile_stats_fold<D>(ct, acc, a.SL, do_pairs, nh ? q : 0, nh, tid);
     if (scalar_sums) tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
@@ -237,7 +260,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
 template <bool TDIST, bool VVV>
 void launch_sweep_t(const SweepArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
-  const SweepSmem L = sweep_smem_layout(D, a.PL.q, a.PL.nl, D * (D + 1) / 2, a.SL.E, TDIST, VVV, a.SL.nlT > 1);
+  const SweepSmem L = sweep_smem_layout(D, a.PL.q, a.PL.nl, D * (D + 1) / 2, a.SL.E, TDIST, VVV, a.SL.nlT > 1, a.maxdeg);
   static size_t attr = 0;
   if (L.bytes > attr) {
     cudaFuncSetAttribute(k_sweep<D, TDIST, VVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.bytes);
@@ -252,7 +275,7 @@ void launch_sweep(int tdist, int vvv, const SweepArgs &a, int grid, cudaStream_t
 }
 
 size_t sweep_smem(int tdist, int vvv, const SweepArgs &a) {
-  return sweep_smem_layout(BSB_D, a.PL.q, a.PL.nl, BSB_D * (BSB_D + 1) / 2, a.SL.E, tdist, vvv, a.SL.nlT > 1).bytes;
+  return sweep_smem_layout(BSB_D, a.PL.q, a.PL.nl, BSB_D * (BSB_D + 1) / 2, a.SL.E, tdist, vvv, a.SL.nlT > 1, a.maxdeg).bytes;
 }
 
 int sweep_max_blocks(int tdist, int vvv, size_t smem) {

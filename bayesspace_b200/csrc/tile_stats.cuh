@@ -22,11 +22,27 @@
 
 namespace bsb {
 
+// Ampere-style asynchronous global -> shared copies (LDGSTS): no register staging, no scoreboard stall.
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// DMMA output tiles kept per warp: the upper 8x8 tiles of U U^T plus nh label tiles per row tile.
+__host__ __device__ inline int stats_frags(int D, int nh) {
+  const int NT = (D + 1 + 7) / 8;
+  return NT * (NT + 1) / 2 + nh * NT;
+}
+
 template <int D>
 struct TileGeom {
   static constexpr int NT = (D + 1 + 7) / 8;      // 8-row tiles of the staged rows: d PCs, then sqrt(w)
   static constexpr int DP = NT * 8;               // padded rows of the shared-memory tile
-  static constexpr int NFRAG = NT * (NT + 1) / 2 + 2 * NT;   // output tiles per warp incl. 2 label tiles per row tile
   static constexpr int NTILES = NT * (NT + 1) / 2;   // upper-triangular 8x8 output tiles
   static constexpr int NP = D * (D + 1) / 2;
 };
@@ -49,10 +65,23 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 // A fragment: lane holds U[8i + (lane>>2)][t0 + (lane&3)]; the B fragment of row-tile j is the same
 // register as the A fragment of row-tile j, so NT loads feed all the DMMAs of a group of 4 spots.
 template <int D>
-__device__ __forceinline__ void tile_stats_mma(double (&C)[TileGeom<D>::NTILES][2], double (&CH)[TileGeom<D>::NT][2][2],
-                                               const double *tile, const uint8_t *zs, bool do_pairs, int nh, int warp,
-                                               int lane) {
-  constexpr int NT = TileGeom<D>::NT, NW = kBlock / 32;
+__device__ __forceinline__ void tile_stats_mma(double *cacc, const double *tile, const uint8_t *zs, bool do_pairs, int nh,
+                                               int warp, int lane) {
+  constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, NW = kBlock / 32;
+  const int NFRAG = stats_frags(D, nh);
+  // The output tiles live in shared memory between tiles (warp-private, 2 doubles per lane and tile): they are
+  // only in registers while the DMMAs run, which keeps the per-spot phase of the kernel below 128 registers.
+  double2 *mine = reinterpret_cast<double2 *>(cacc + (size_t) warp * NFRAG * 64 + (lane >> 2) * 8 + 2 * (lane & 3));
+  double C[NTILES][2], CH[NT][2][2];
+#pragma unroll
+  for (int t = 0; t < NTILES; t++) { const double2 v = mine[t * 32]; C[t][0] = v.x; C[t][1] = v.y; }
+#pragma unroll
+  for (int i = 0; i < NT; i++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (h < nh) { const double2 v = mine[(NTILES + h * NT + i) * 32]; CH[i][h][0] = v.x; CH[i][h][1] = v.y; }
+      else CH[i][h][0] = CH[i][h][1] = 0.0;
+    }
   const double *base = tile + (lane >> 2) * kTileLd + (lane & 3);
   const double *swrow = tile + D * kTileLd + (lane & 3);
   const int kc = lane >> 2;
@@ -80,28 +109,21 @@ __device__ __forceinline__ void tile_stats_mma(double (&C)[TileGeom<D>::NTILES][
       for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][1], f[i], h1);
     }
   }
-}
-
-// Segment end: fold the warps' output tiles (fixed order) into the record.  scratch: NW * NFRAG * 64 doubles
-// (may alias the tile).  Contains two __syncthreads().
-template <int D>
-__device__ __forceinline__ void tile_stats_fold(const double (&C)[TileGeom<D>::NTILES][2],
-                                                const double (&CH)[TileGeom<D>::NT][2][2], double *scratch, double *acc,
-                                                const StatLayout &SL, bool do_pairs, int q, int tid) {
-  constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, NP = TileGeom<D>::NP, NW = kBlock / 32;
-  constexpr int NFRAG = TileGeom<D>::NFRAG;
-  const int warp = tid >> 5, lane = tid & 31;
-  __syncthreads();   // the tile may be aliased by scratch
-  double *mine = scratch + (size_t) warp * NFRAG * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
 #pragma unroll
-  for (int t = 0; t < NTILES; t++) { mine[t * 64] = C[t][0]; mine[t * 64 + 1] = C[t][1]; }
+  for (int t = 0; t < NTILES; t++) mine[t * 32] = make_double2(C[t][0], C[t][1]);
 #pragma unroll
   for (int i = 0; i < NT; i++)
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      mine[(NTILES + 2 * i + h) * 64] = CH[i][h][0];
-      mine[(NTILES + 2 * i + h) * 64 + 1] = CH[i][h][1];
-    }
+    for (int h = 0; h < 2; h++)
+      if (h < nh) mine[(NTILES + h * NT + i) * 32] = make_double2(CH[i][h][0], CH[i][h][1]);
+}
+
+// Segment end: fold the warps' output tiles (fixed order) into the record.  Contains a __syncthreads().
+template <int D>
+__device__ __forceinline__ void tile_stats_fold(const double *cacc, double *acc, const StatLayout &SL, bool do_pairs,
+                                                int q, int nh, int tid) {
+  constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, NP = TileGeom<D>::NP, NW = kBlock / 32;
+  const int NFRAG = stats_frags(D, nh);
   __syncthreads();
   if (do_pairs)
     for (int p = tid; p < NP; p += kBlock) {
@@ -111,15 +133,15 @@ __device__ __forceinline__ void tile_stats_fold(const double (&C)[TileGeom<D>::N
       const int t = i * NT - i * (i - 1) / 2 + (j - i);
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < NW; w++) s += scratch[((size_t) w * NFRAG + t) * 64 + (a & 7) * 8 + (b & 7)];
+      for (int w = 0; w < NW; w++) s += cacc[((size_t) w * NFRAG + t) * 64 + (a & 7) * 8 + (b & 7)];
       acc[SL.T + p] = s;
     }
   for (int e = tid; e < q * (D + 1); e += kBlock) {   // (cluster k, row a): a < D -> s_k[a], a == D -> n_k
     const int k = e / (D + 1), a = e - k * (D + 1);
-    const int t = NTILES + 2 * (a >> 3) + (k >> 3);
+    const int t = NTILES + (k >> 3) * NT + (a >> 3);
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; w++) s += scratch[((size_t) w * NFRAG + t) * 64 + (a & 7) * 8 + (k & 7)];
+    for (int w = 0; w < NW; w++) s += cacc[((size_t) w * NFRAG + t) * 64 + (a & 7) * 8 + (k & 7)];
     if (a < D) acc[SL.sk + k * D + a] = s;
     else acc[SL.nk + k] = s;
   }
