@@ -144,7 +144,7 @@ struct bsb200_chain {
   cudaGraphExec_t graph_iter = nullptr, graph_batch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t iters_done = 0;
-  int blocks_per_sm = 1;
+  int blocks_per_sm = 1, kernels_per_iter = 0;
   double setup_ms = 0;
 
   ~bsb200_chain() {
@@ -231,9 +231,11 @@ static int check_device_error(bsb200_chain *ch) {
 
 static int build_graphs(bsb200_chain *ch) {
   cudaGraph_t g = nullptr;
+  const long long launches_before = g_launches.load();
   CK(cudaStreamBeginCapture(ch->stream, cudaStreamCaptureModeThreadLocal));
   ch->enqueue_iteration(ch->stream);
   CK(cudaStreamEndCapture(ch->stream, &g));
+  ch->kernels_per_iter = (int) (g_launches.load() - launches_before);   // kernel nodes of one iteration
   CK(cudaGraphInstantiate(&ch->graph_iter, g, 0));
   cudaGraphDestroy(g);
   if (ch->thin > 1 && ch->thin <= 256 && ch->n <= 200000) {   // launch-bound sizes: one graph per thin batch
@@ -243,6 +245,7 @@ static int build_graphs(bsb200_chain *ch) {
     CK(cudaGraphInstantiate(&ch->graph_batch, g, 0));
     cudaGraphDestroy(g);
   }
+  g_launches.store(launches_before);   // captured nodes are counted when the graphs are launched
   return BSB200_OK;
 }
 
@@ -413,6 +416,7 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     } else {
       for (int64_t i = 0; i < run; i++) CK(cudaGraphLaunch(ch->graph_iter, s));
     }
+    g_launches += (long long) ch->kernels_per_iter * run;
     ch->iters_done += run;
     remaining -= run;
     const bool boundary = (ch->iters_done + 1) % ch->thin == 0;

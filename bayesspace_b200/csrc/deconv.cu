@@ -227,6 +227,7 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
       if (k.nseg > 0) { K.deconv(k, k.nseg, s); g_launches++; }
     }
   };
+  int kernels_per_iter = 0;
   param_kernel_init();
   {   // statistics of the initial state
     DeconvArgs k = deconv_args(-1, 1);
@@ -237,9 +238,11 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
   CK(cudaGetLastError());
   {
     cudaGraph_t g = nullptr;
+    const long long launches_before = g_launches.load();
     CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     enqueue_iteration();
     CK(cudaStreamEndCapture(s, &g));
+    kernels_per_iter = (int) (g_launches.load() - launches_before);
     CK(cudaGraphInstantiate(&run.graph_iter, g, 0));
     cudaGraphDestroy(g);
     if (a->thin > 1 && a->thin <= 256 && n <= 400000) {
@@ -249,6 +252,7 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
       CK(cudaGraphInstantiate(&run.graph_batch, g, 0));
       cudaGraphDestroy(g);
     }
+    g_launches.store(launches_before);
   }
   // ---- row 0 of the outputs (:793-801) -------------------------------------------------------------
   if (out->z) {
@@ -277,6 +281,7 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
     CK(cudaEventRecord(run.ev0, s));
     if (runit == a->thin && run.graph_batch) CK(cudaGraphLaunch(run.graph_batch, s));
     else for (int64_t i = 0; i < runit; i++) CK(cudaGraphLaunch(run.graph_iter, s));
+    g_launches += (long long) kernels_per_iter * runit;
     done += runit;
     remaining -= runit;
     const bool boundary = (done + 1) % a->thin == 0;

@@ -119,11 +119,11 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
         const int64_t pj = (int64_t) begin + pbase + tid;
         const double *src = a.Y + pj;
         double *dst = tile0 + buf * DP * kTileLd + tid;
-#pragma unroll 1
-        for (int c = 0; c < D; c++, src += a.ld, dst += kTileLd) cp_async8(dst, src);   // rolled: no hoisted addresses
+#pragma unroll
+        for (int c = 0; c < D; c++, src += a.ld, dst += kTileLd) cp_async8(dst, src);
         const int32_t *esrc = a.ell + pj;
         int32_t *edst = ellbuf + buf * a.maxdeg * kBlock + tid;
-#pragma unroll 1
+#pragma unroll 4
         for (int e = 0; e < a.maxdeg; e++, esrc += a.ld, edst += kBlock) cp_async4(edst, esrc);
         cp_async4(origbuf + buf * kBlock + tid, a.orig + pj);
       }
