@@ -89,6 +89,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per sweep launch from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r1_sweep_%s_ncu.json" % name)
+    try:
+        return float(json.load(open(p))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def build_workload(name):
     import bayesspace_b200 as B
     from bayesspace_b200 import synth
@@ -261,7 +270,8 @@ def run_gpu(args):
                                       if world > 1 else "single chain, 1 GPU",
                                       sweeps_per_s=world * K / (ms * 1e-3), colours=colour[1]),
             "roofline": {"bound": "hbm", "kernel": "k_sweep<%d,t,shared>" % w.d, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(args.workload),
+                         "traffic_source": "profiles/r1_sweep_%s_ncu.json (ncu --set full, bytes per launch)" % args.workload,
                          "algorithmic_bytes_per_spot_update": Bspot, "bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sweep_ms_per_launch, "formula": ALGO_NOTE,
                          "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50))},
