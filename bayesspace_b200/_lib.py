@@ -32,13 +32,14 @@ class ClusterArgs(C.Structure):
                 ("alpha", C.c_double), ("beta", C.c_double), ("Y", C.c_void_p), ("nbr_ptr", C.c_void_p),
                 ("nbr_idx", C.c_void_p), ("init", C.c_void_p), ("mu0", C.c_void_p), ("lambda0", C.c_void_p),
                 ("seed", C.c_uint64), ("compat", C.c_uint32), ("device", C.c_int32), ("colour", C.c_void_p),
-                ("ncolours", C.c_int32), ("reserved", C.c_int32)]
+                ("ncolours", C.c_int32), ("groups", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
+                ("comm_id", C.c_void_p)]
 
 
 class ClusterOut(C.Structure):
     _fields_ = [("z", C.c_void_p), ("mu", C.c_void_p), ("lambda_", C.c_void_p), ("weights", C.c_void_p),
                 ("plogLik", C.c_void_p), ("rows_done", C.c_int32), ("ncolours", C.c_int32),
-                ("setup_ms", C.c_double), ("device_ms", C.c_double)]
+                ("setup_ms", C.c_double), ("device_ms", C.c_double), ("own_lo", C.c_int64), ("own_hi", C.c_int64)]
 
 
 class DeconvArgs(C.Structure):
@@ -63,7 +64,7 @@ EXPORTS = [
     "bsb200_version", "bsb200_last_error", "bsb200_cancel", "bsb200_device_count",
     "bsb200_neighbors_lattice", "bsb200_neighbors_radius", "bsb200_parse_neighbor_strings",
     "bsb200_subspot_neighbors", "bsb200_neighbors_to_matrix4", "bsb200_colour_graph", "bsb200_colour_lattice",
-    "bsb200_cluster", "bsb200_chain_create", "bsb200_chain_run", "bsb200_chain_profile", "bsb200_chain_state",
+    "bsb200_cluster", "bsb200_comm_unique_id", "bsb200_shard_plan", "bsb200_chain_create", "bsb200_chain_run", "bsb200_chain_profile", "bsb200_chain_state",
     "bsb200_chain_destroy", "bsb200_kernel_launches", "bsb200_eval_loglik", "bsb200_eval_suffstats",
     "bsb200_chain_dry_sweep", "bsb200_debug_rng", "bsb200_deconv",
 ]

@@ -1,6 +1,7 @@
 // chain.cu -- host layer of the four cluster samplers behind the C ABI (include/bsb200.h):
-// argument validation, colouring / ordering / segmentation of the spots, HBM staging, the
-// per-iteration launch schedule (captured once as a CUDA graph), snapshots and error mapping.
+// argument validation, colouring / ordering / segmentation of the spots, spot sharding over several
+// GPUs, HBM staging, the per-iteration launch schedule (captured once as a CUDA graph, NCCL exchanges
+// included), snapshots and error mapping.
 //
 // Replaces the bodies of iterate / iterate_vvv / iterate_t / iterate_t_vvv
 // (/root/reference/src/cluster.cpp:217-710) as seen through their Rcpp glue
@@ -12,6 +13,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+
+#include "comm.hpp"
+#include "shard.hpp"
 
 namespace bsb {
 
@@ -52,39 +56,42 @@ int select_device(int device) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Spot ordering: internal order = (group, colour, original index); segments = runs of at most
-// `seg` spots inside one (group, colour) range; slots numbered in internal order so that every
-// group's partial records are contiguous.
+// Spot ordering of the spots [lo, hi) a rank owns: internal order = (group, colour, original id);
+// segments = runs of at most `seg` spots inside one (group, colour) range; slots numbered in internal
+// order so that every group's partial records are contiguous.  Groups are global (virtual shards).
 // ------------------------------------------------------------------------------------------------
-int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups_req, int seg_spots) {
+int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups_total, int seg_spots, int g0, int g1,
+                     int64_t lo, int64_t hi) {
+  if (g1 < 0) { g0 = 0; g1 = ngroups_total; lo = 0; hi = n; }
   ncol = ncolours;
-  ngroups = ngroups_req;
-  perm.resize((size_t) n);
-  inv.resize((size_t) n);
+  ngroups = g1 - g0;
+  const int64_t n_own = hi - lo;
+  perm.resize((size_t) n_own);
+  inv.resize((size_t) n_own);
   std::vector<int64_t> bucket((size_t) ngroups * ncol + 1, 0);
-  auto grp = [&](int64_t j) { return (int) ((j * (int64_t) ngroups) / n); };
-  for (int64_t j = 0; j < n; j++) bucket[(size_t) grp(j) * ncol + colour[j] + 1]++;
+  auto grp = [&](int64_t j) { return (int) ((j * (int64_t) ngroups_total) / n) - g0; };
+  for (int64_t j = lo; j < hi; j++) bucket[(size_t) grp(j) * ncol + colour[j] + 1]++;
   for (size_t b = 0; b < bucket.size() - 1; b++) bucket[b + 1] += bucket[b];
   std::vector<int64_t> fill(bucket.begin(), bucket.end() - 1);
-  for (int64_t j = 0; j < n; j++) {
+  for (int64_t j = lo; j < hi; j++) {
     const int64_t pos = fill[(size_t) grp(j) * ncol + colour[j]]++;
     perm[(size_t) pos] = (int32_t) j;
-    inv[(size_t) j] = (int32_t) pos;
+    inv[(size_t) (j - lo)] = (int32_t) pos;
   }
   seg_begin.clear(); seg_count.clear(); seg_slot.clear();
   colour_seg_start.assign((size_t) ncol + 1, 0);
   group_start.assign((size_t) ngroups + 1, 0);
   // slots in (group, colour) order; launch lists in (colour, group) order
-  std::vector<std::vector<int32_t>> per_colour_begin((size_t) ncol), per_colour_count((size_t) ncol), per_colour_slot((size_t) ncol);
+  std::vector<std::vector<int32_t>> cb((size_t) ncol), cc((size_t) ncol), cs((size_t) ncol);
   int32_t slot = 0;
   for (int g = 0; g < ngroups; g++) {
     group_start[(size_t) g] = slot;
     for (int c = 0; c < ncol; c++) {
       const int64_t b = bucket[(size_t) g * ncol + c], e = bucket[(size_t) g * ncol + c + 1];
       for (int64_t s = b; s < e; s += seg_spots) {
-        per_colour_begin[(size_t) c].push_back((int32_t) s);
-        per_colour_count[(size_t) c].push_back((int32_t) std::min<int64_t>(seg_spots, e - s));
-        per_colour_slot[(size_t) c].push_back(slot++);
+        cb[(size_t) c].push_back((int32_t) s);
+        cc[(size_t) c].push_back((int32_t) std::min<int64_t>(seg_spots, e - s));
+        cs[(size_t) c].push_back(slot++);
       }
     }
   }
@@ -92,9 +99,9 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
   nslots = slot;
   for (int c = 0; c < ncol; c++) {
     colour_seg_start[(size_t) c] = (int32_t) seg_begin.size();
-    seg_begin.insert(seg_begin.end(), per_colour_begin[(size_t) c].begin(), per_colour_begin[(size_t) c].end());
-    seg_count.insert(seg_count.end(), per_colour_count[(size_t) c].begin(), per_colour_count[(size_t) c].end());
-    seg_slot.insert(seg_slot.end(), per_colour_slot[(size_t) c].begin(), per_colour_slot[(size_t) c].end());
+    seg_begin.insert(seg_begin.end(), cb[(size_t) c].begin(), cb[(size_t) c].end());
+    seg_count.insert(seg_count.end(), cc[(size_t) c].begin(), cc[(size_t) c].end());
+    seg_slot.insert(seg_slot.end(), cs[(size_t) c].begin(), cs[(size_t) c].end());
   }
   colour_seg_start[(size_t) ncol] = (int32_t) seg_begin.size();
   return BSB200_OK;
@@ -103,7 +110,7 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
 int choose_groups(int64_t n) { return n >= 262144 ? kGroups : 1; }
 int choose_segment(int64_t n) {
   int64_t tps = n / ((int64_t) kBlock * 2048);
-  tps = std::max<int64_t>(1, std::min<int64_t>(8, tps));
+  tps = std::max<int64_t>(1, std::min<int64_t>(16, tps));
   return (int) tps * kBlock;
 }
 
@@ -122,20 +129,23 @@ using namespace bsb;
 struct bsb200_chain {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int64_t n = 0, ld = 0;
-  int d = 0, q = 0, nl = 1, maxdeg = 0;
+  int64_t n = 0, n_own = 0, ld = 0, lo = 0, hi = 0;
+  int d = 0, q = 0, nl = 1, maxdeg = 0, G = 1;
   bool tdist = false, vvv = false;
   uint32_t compat = 0, sweep_flags = 0;
   int nrep = 0, thin = 1;
   double gamma = 0, alpha = 0, beta = 0;
   uint64_t seed = 0;
+  ShardPlan plan;
+  HaloPlan halo;
+  Comm comm;
   SpotOrder ord;
   ParamLayout PL;
   StatLayout SL;
   KernelsForD K{};
   DevBuf<double> Y, w, params, partials, gsum, stats, T_fixed, mu0c, lambda0, lm0, ybar, plogLik, snap_mu, snap_lambda, snap_w;
-  DevBuf<uint8_t> z;
-  DevBuf<int32_t> ell, orig, seg_begin, seg_count, seg_slot, group_start, snap_z;
+  DevBuf<uint8_t> z, halo_send, halo_recv;
+  DevBuf<int32_t> ell, orig, seg_begin, seg_count, seg_slot, group_start, snap_z, send_pos, recv_pos;
   DevBuf<uint32_t> iter;
   DevBuf<int> err;
   std::vector<double> ybar_host;
@@ -144,8 +154,9 @@ struct bsb200_chain {
   cudaGraphExec_t graph_iter = nullptr, graph_batch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t iters_done = 0;
-  int blocks_per_sm = 1, kernels_per_iter = 0;
+  int kernels_per_iter = 0;
   double setup_ms = 0;
+  int comm_rc = 0;               // first NCCL failure seen while enqueuing (reported by the next sync point)
 
   ~bsb200_chain() {
     if (graph_iter) cudaGraphExecDestroy(graph_iter);
@@ -156,6 +167,8 @@ struct bsb200_chain {
     if (h_snap_w) cudaFreeHost(h_snap_w);
     if (stream) cudaStreamDestroy(stream);
   }
+
+  int world() const { return plan.world; }
 
   SweepArgs sweep_args(int colour, uint32_t flags, uint32_t iter_add) const {
     SweepArgs a{};
@@ -173,7 +186,7 @@ struct bsb200_chain {
   ParamArgs param_args(bool finalize_only) const {
     ParamArgs a{};
     a.PL = PL; a.SL = SL; a.params = params.p; a.partials = partials.p; a.group_start = group_start.p;
-    a.ngroups = ord.ngroups; a.gsum = gsum.p; a.gsum_ready = ord.ngroups > 1; a.stats = stats.p;
+    a.ngroups = G; a.gsum = gsum.p; a.gsum_ready = G > 1; a.stats = stats.p;
     a.T_fixed = T_fixed.p; a.mu0c = mu0c.p; a.lambda0 = lambda0.p; a.lm0 = lm0.p; a.ybar = ybar.p;
     a.alpha = alpha; a.beta = beta; a.n = n; a.tdist = tdist; a.vvv = vvv; a.compat = compat;
     a.key0 = (uint32_t) seed; a.key1 = (uint32_t) (seed >> 32);
@@ -182,8 +195,15 @@ struct bsb200_chain {
     a.finalize_only = finalize_only; a.precision_form = 0; a.err = err.p;
     return a;
   }
+  // level 1 of the statistics fold on the shards this rank owns, allgather of the shard sums, k_param
   void enqueue_reduce_and_param(bool finalize_only, cudaStream_t s) {
-    if (ord.ngroups > 1) launch_reduce_groups(partials.p, group_start.p, ord.ngroups, SL.E, gsum.p, s);
+    if (G > 1) {
+      launch_reduce_groups(partials.p, group_start.p, ord.ngroups, SL.E, gsum.p + (size_t) plan.g0 * SL.E, s);
+      if (world() > 1) {
+        int rc = comm.allgather_f64(gsum.p, (size_t) ord.ngroups * SL.E, s);
+        if (rc && !comm_rc) comm_rc = rc;
+      }
+    }
     launch_param(param_args(finalize_only), s);
     g_launches++;
   }
@@ -193,9 +213,23 @@ struct bsb200_chain {
     K.sweep(tdist, vvv, a, a.nseg, s);
     g_launches++;
   }
+  // labels of the boundary spots of one colour travel to the ranks that hold them as ghosts
+  void enqueue_halo(int colour, cudaStream_t s) {
+    if (world() <= 1) return;
+    const int W = world();
+    const int32_t *so = halo.send_off.data() + (size_t) colour * W, *ro = halo.recv_off.data() + (size_t) colour * W;
+    const int ns = so[W] - so[0], nr = ro[W] - ro[0];
+    launch_halo_pack(z.p, send_pos.p + so[0], ns, halo_send.p + so[0], s);
+    int rc = comm.exchange_u8(halo_send.p, so, halo_recv.p, ro, s);
+    if (rc && !comm_rc) comm_rc = rc;
+    launch_halo_unpack(z.p, recv_pos.p + ro[0], nr, halo_recv.p + ro[0], s);
+  }
   void enqueue_iteration(cudaStream_t s) {
     enqueue_reduce_and_param(false, s);
-    for (int c = 0; c < ord.ncol; c++) enqueue_sweep(c, 0, 0, s);
+    for (int c = 0; c < ord.ncol; c++) {
+      enqueue_sweep(c, 0, 0, s);
+      enqueue_halo(c, s);
+    }
   }
 };
 
@@ -224,6 +258,7 @@ static int check_device_error(bsb200_chain *ch) {
   int e = 0;
   CK(cudaMemcpyAsync(&e, ch->err.p, sizeof(int), cudaMemcpyDeviceToHost, ch->stream));
   CK(cudaStreamSynchronize(ch->stream));
+  if (ch->comm_rc) return ch->comm_rc;
   if (e == BSB_DEVERR_NUMERIC)
     return fail(BSB200_ERR_NUMERIC, "NA in probability vector, empty cluster (Wishart df <= 0) or matrix not positive definite");
   return BSB200_OK;
@@ -238,7 +273,7 @@ static int build_graphs(bsb200_chain *ch) {
   ch->kernels_per_iter = (int) (g_launches.load() - launches_before);   // kernel nodes of one iteration
   CK(cudaGraphInstantiate(&ch->graph_iter, g, 0));
   cudaGraphDestroy(g);
-  if (ch->thin > 1 && ch->thin <= 256 && ch->n <= 200000) {   // launch-bound sizes: one graph per thin batch
+  if (ch->thin > 1 && ch->thin <= 256 && ch->n <= 200000 && ch->world() == 1) {   // launch-bound sizes: one graph per thin batch
     CK(cudaStreamBeginCapture(ch->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < ch->thin; i++) ch->enqueue_iteration(ch->stream);
     CK(cudaStreamEndCapture(ch->stream, &g));
@@ -246,6 +281,7 @@ static int build_graphs(bsb200_chain *ch) {
     cudaGraphDestroy(g);
   }
   g_launches.store(launches_before);   // captured nodes are counted when the graphs are launched
+  if (ch->comm_rc) return ch->comm_rc;
   return BSB200_OK;
 }
 
@@ -265,13 +301,23 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   ch->nl = ch->vvv ? a->q : 1;
   ch->compat = a->compat; ch->nrep = a->nrep; ch->thin = a->thin;
   ch->gamma = a->gamma; ch->alpha = a->alpha; ch->beta = a->beta; ch->seed = a->seed;
-  ch->ld = (a->n + 31) / 32 * 32;
   const int64_t n = a->n;
   const int d = a->d, q = a->q;
   if ((a->compat & BSB200_COMPAT_Q3) && ch->vvv && !ch->tdist) ch->sweep_flags |= SW_Q3;
   if (!ch->tdist && !ch->vvv) ch->sweep_flags |= SW_NO_PAIRS;
 
-  // ---- colouring -------------------------------------------------------------------------------
+  // ---- sharding ----------------------------------------------------------------------------------
+  const int world = a->world > 1 ? a->world : 1, rank = world > 1 ? a->rank : 0;
+  const int G = a->groups > 0 ? a->groups : (world > 1 ? kGroups : choose_groups(n));
+  if (G > 4096) return fail(BSB200_ERR_INVALID, "groups = %d out of range", G);
+  rc = make_shard_plan(n, a->nbr_ptr, a->nbr_idx, G, world, rank, ch->plan);
+  if (rc) return rc;
+  const ShardPlan &plan = ch->plan;
+  ch->G = G; ch->lo = plan.lo; ch->hi = plan.hi; ch->n_own = plan.n_own();
+  const int64_t n_own = ch->n_own, n_local = plan.n_local();
+  ch->ld = (n_local + 31) / 32 * 32;
+
+  // ---- colouring (of the whole graph: every rank derives the same classes) ------------------------
   std::vector<int32_t> colour;
   int32_t ncol = 0;
   if (a->colour) {
@@ -281,15 +327,21 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     for (int64_t j = 0; j < n; j++)
       if (colour[(size_t) j] < 0 || colour[(size_t) j] >= ncol) return fail(BSB200_ERR_INVALID, "colour[%lld] out of range", (long long) j);
     if (!colouring_is_proper(a->nbr_ptr, a->nbr_idx, n, colour.data())) {
-      colour.clear();   // e.g. hex offsets on a filled rectangle: fall back to greedy
+      colour.clear();   // e.g. hex offsets on a filled rectangle: colour the graph ourselves
     }
   }
   if (colour.empty()) {
     rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
     if (rc) return rc;
   }
-  ch->ord.build(n, colour.data(), ncol, choose_groups(n), choose_segment(n));
+  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n), plan.g0, plan.g1, plan.lo, plan.hi);
   const SpotOrder &ord = ch->ord;
+  if (world > 1) {
+    rc = make_halo_plan(plan, a->nbr_ptr, a->nbr_idx, colour.data(), ncol, ord.inv, ch->halo);
+    if (rc) return rc;
+    rc = ch->comm.init(world, rank, a->comm_id);
+    if (rc) return rc;
+  }
 
   // ---- device staging --------------------------------------------------------------------------
   CK(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
@@ -302,16 +354,24 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   {
     std::vector<int32_t> ell((size_t) std::max(maxdeg, 1) * ch->ld, -1);
     std::vector<uint8_t> z0((size_t) ch->ld, 0);
-    for (int64_t i = 0; i < n; i++) {
+    for (int64_t i = 0; i < n_own; i++) {
       const int64_t j = ord.perm[(size_t) i];
       z0[(size_t) i] = (uint8_t) (a->init[j] - 1);
       int e = 0;
-      for (int64_t p = a->nbr_ptr[j]; p < a->nbr_ptr[j + 1]; p++, e++) ell[(size_t) e * ch->ld + i] = ord.inv[(size_t) a->nbr_idx[p]];
+      for (int64_t p = a->nbr_ptr[j]; p < a->nbr_ptr[j + 1]; p++, e++) {
+        const int32_t u = a->nbr_idx[p];
+        int32_t pos;
+        if (u >= plan.lo && u < plan.hi) pos = ord.inv[(size_t) (u - plan.lo)];
+        else pos = (int32_t) (n_own + (std::lower_bound(plan.ghosts.begin(), plan.ghosts.end(), u) - plan.ghosts.begin()));
+        ell[(size_t) e * ch->ld + i] = pos;
+      }
     }
+    for (size_t gi = 0; gi < plan.ghosts.size(); gi++) z0[(size_t) n_own + gi] = (uint8_t) (a->init[plan.ghosts[gi]] - 1);
     if ((rc = upload(ch->ell, ell.data(), ell.size(), s))) return rc;
     if ((rc = upload(ch->z, z0.data(), z0.size(), s))) return rc;
     std::vector<int32_t> origp((size_t) ch->ld, 0);
     std::copy(ord.perm.begin(), ord.perm.end(), origp.begin());
+    std::copy(plan.ghosts.begin(), plan.ghosts.end(), origp.begin() + n_own);
     if ((rc = upload(ch->orig, origp.data(), origp.size(), s))) return rc;
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }
@@ -319,16 +379,36 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if ((rc = upload(ch->seg_count, ord.seg_count.data(), ord.seg_count.size(), s))) return rc;
   if ((rc = upload(ch->seg_slot, ord.seg_slot.data(), ord.seg_slot.size(), s))) return rc;
   if ((rc = upload(ch->group_start, ord.group_start.data(), ord.group_start.size(), s))) return rc;
+  if (world > 1) {
+    if ((rc = upload(ch->send_pos, ch->halo.send_pos.data(), ch->halo.send_pos.size(), s))) return rc;
+    if ((rc = upload(ch->recv_pos, ch->halo.recv_pos.data(), ch->halo.recv_pos.size(), s))) return rc;
+    if ((rc = ch->halo_send.alloc(ch->halo.send_pos.size())) || (rc = ch->halo_recv.alloc(ch->halo.recv_pos.size()))) return rc;
+  }
   {
-    DevBuf<double> Yraw;
-    if ((rc = upload(Yraw, a->Y, (size_t) n * d, s))) return rc;
-    if ((rc = ch->ybar.alloc((size_t) d))) return rc;
-    if ((rc = ch->Y.alloc((size_t) d * ch->ld))) return rc;
+    // own rows of Y (R's column-major n x d): one strided copy; column means from per-shard sums
+    DevBuf<double> Yraw, gcol;
+    DevBuf<int64_t> glo;
+    if ((rc = Yraw.alloc((size_t) n_own * d)) || (rc = gcol.alloc((size_t) G * d)) || (rc = ch->ybar.alloc((size_t) d)) ||
+        (rc = ch->Y.alloc((size_t) d * ch->ld)))
+      return rc;
+    CK(cudaMemcpy2DAsync(Yraw.p, sizeof(double) * n_own, a->Y + plan.lo, sizeof(double) * n, sizeof(double) * n_own, (size_t) d,
+                         cudaMemcpyHostToDevice, s));
+    if ((rc = upload(glo, plan.group_lo.data(), plan.group_lo.size(), s))) return rc;
     CK(cudaMemsetAsync(ch->Y.p, 0, sizeof(double) * d * ch->ld, s));
-    launch_colmeans(Yraw.p, n, d, ch->ybar.p, s);
-    launch_permute_center(Yraw.p, n, n, d, ch->orig.p, ch->ybar.p, ch->Y.p, ch->ld, s);
-    ch->ybar_host.resize((size_t) d);
-    CK(cudaMemcpyAsync(ch->ybar_host.data(), ch->ybar.p, sizeof(double) * d, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemsetAsync(gcol.p, 0, sizeof(double) * G * d, s));
+    launch_colsums_groups(Yraw.p, n_own, glo.p, plan.lo, d, plan.g0, plan.g1 - plan.g0, gcol.p, s);
+    if (world > 1 && (rc = ch->comm.allgather_f64(gcol.p, (size_t) (plan.g1 - plan.g0) * d, s))) return rc;
+    std::vector<double> gs((size_t) G * d);
+    CK(cudaMemcpyAsync(gs.data(), gcol.p, sizeof(double) * G * d, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ch->ybar_host.assign((size_t) d, 0.0);
+    for (int c = 0; c < d; c++) {
+      double acc = 0.0;
+      for (int g = 0; g < G; g++) acc += gs[(size_t) g * d + c];   // shard order: independent of the GPU count
+      ch->ybar_host[(size_t) c] = acc / (double) n;
+    }
+    CK(cudaMemcpyAsync(ch->ybar.p, ch->ybar_host.data(), sizeof(double) * d, cudaMemcpyHostToDevice, s));
+    launch_permute_center(Yraw.p, n_own, n_own, d, ch->orig.p, ch->ybar.p, ch->Y.p, ch->ld, s, plan.lo);
     CK(cudaStreamSynchronize(s));
   }
   {
@@ -354,19 +434,20 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   const StatLayout SL_run = make_stat_layout(q, d, nlT);
   const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
   const size_t Emax = (size_t) std::max(SL_run.E, SL_init.E);
-  if ((rc = ch->partials.alloc((size_t) ord.nslots * Emax))) return rc;
-  if ((rc = ch->gsum.alloc((size_t) ord.ngroups * Emax))) return rc;
+  if ((rc = ch->partials.alloc((size_t) std::max(ord.nslots, 1) * Emax))) return rc;
+  if ((rc = ch->gsum.alloc((size_t) G * Emax))) return rc;
   if ((rc = ch->stats.alloc(Emax))) return rc;
   if ((rc = ch->T_fixed.alloc((size_t) ch->PL.np))) return rc;
   if ((rc = ch->plogLik.alloc((size_t) a->nrep))) return rc;
   if ((rc = ch->snap_mu.alloc((size_t) nsnap * q * d))) return rc;
   if ((rc = ch->snap_lambda.alloc((size_t) nsnap * ch->nl * d * d))) return rc;
-  if ((rc = ch->snap_z.alloc((size_t) n))) return rc;
-  if ((rc = ch->snap_w.alloc((size_t) n))) return rc;
+  if ((rc = ch->snap_z.alloc((size_t) n_own))) return rc;
+  if ((rc = ch->snap_w.alloc((size_t) n_own))) return rc;
   if ((rc = ch->iter.alloc(1))) return rc;
   if ((rc = ch->err.alloc(1))) return rc;
   CK(cudaMemsetAsync(ch->iter.p, 0, sizeof(uint32_t), s));
   CK(cudaMemsetAsync(ch->err.p, 0, sizeof(int), s));
+  CK(cudaMemsetAsync(ch->gsum.p, 0, sizeof(double) * G * Emax, s));
   CK(cudaMemsetAsync(ch->snap_mu.p, 0, sizeof(double) * nsnap * q * d, s));
   CK(cudaMemsetAsync(ch->snap_lambda.p, 0, sizeof(double) * nsnap * ch->nl * d * d, s));
   {
@@ -374,10 +455,11 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     CK(cudaMemcpyAsync(ch->plogLik.p, nanv.data(), sizeof(double) * a->nrep, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
   }
-  CK(cudaMallocHost(&ch->h_snap_z, sizeof(int32_t) * n));
-  CK(cudaMallocHost(&ch->h_snap_w, sizeof(double) * n));
+  CK(cudaMallocHost(&ch->h_snap_z, sizeof(int32_t) * std::max<int64_t>(n_own, 1)));
+  CK(cudaMallocHost(&ch->h_snap_w, sizeof(double) * std::max<int64_t>(n_own, 1)));
 
   // ---- statistics of the initial state -----------------------------------------------------------
+  param_kernel_init();
   if (nlT == 0) {   // normal model, shared precision: sum_j y_j y_j^T never changes -> T_fixed
     ch->SL = SL_init;
     const uint32_t keep = ch->sweep_flags;
@@ -391,7 +473,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   ch->enqueue_sweep(-1, SW_STATS_ONLY, 0, s);
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
-  param_kernel_init();
+  if (ch->comm_rc) return ch->comm_rc;
   if ((rc = build_graphs(ch.get()))) return rc;
   ch->setup_ms = now_ms() - t0;
   *out = ch.release();
@@ -421,10 +503,10 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     remaining -= run;
     const bool boundary = (ch->iters_done + 1) % ch->thin == 0;
     if (boundary) {
-      launch_snapshot(ch->z.p, ch->tdist ? ch->w.p : nullptr, ch->orig.p, ch->n, ch->snap_z.p,
-                      ch->tdist ? ch->snap_w.p : nullptr, s);
-      CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n, cudaMemcpyDeviceToHost, s));
-      if (ch->tdist) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n, cudaMemcpyDeviceToHost, s));
+      launch_snapshot(ch->z.p, ch->tdist ? ch->w.p : nullptr, ch->orig.p, ch->n_own, ch->snap_z.p,
+                      ch->tdist ? ch->snap_w.p : nullptr, s, ch->lo);
+      CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
+      if (ch->tdist) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ch->ev1, s));
     CK(cudaStreamSynchronize(s));
@@ -434,8 +516,8 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     if (boundary) {
       const size_t r = (size_t) ((ch->iters_done + 1) / ch->thin);
       if (out && r < (size_t) (ch->nrep / ch->thin + 1)) {
-        if (out->z) std::memcpy(out->z + r * ch->n, ch->h_snap_z, sizeof(int32_t) * ch->n);
-        if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n, ch->h_snap_w, sizeof(double) * ch->n);
+        if (out->z) std::memcpy(out->z + r * ch->n + ch->lo, ch->h_snap_z, sizeof(int32_t) * ch->n_own);
+        if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n + ch->lo, ch->h_snap_w, sizeof(double) * ch->n_own);
         out->rows_done = (int32_t) r + 1;
       }
       int rc = check_device_error(ch);
@@ -459,6 +541,7 @@ int chain_finish_impl(bsb200_chain *ch, bsb200_cluster_out *out) {
   if (out->mu) CK(cudaMemcpyAsync(out->mu, ch->snap_mu.p, sizeof(double) * nsnap * q * d, cudaMemcpyDeviceToHost, s));
   if (out->lambda) CK(cudaMemcpyAsync(out->lambda, ch->snap_lambda.p, sizeof(double) * nsnap * ch->nl * d * d, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (ch->comm_rc) return ch->comm_rc;
   return BSB200_OK;
 }
 
@@ -501,6 +584,7 @@ int bsb200_chain_profile(bsb200_chain *ch, int32_t iters, double *sweep_ms, int6
       CK(cudaEventRecord(ev[k++], s));
       ch->enqueue_sweep(c, 0, 0, s);
       CK(cudaEventRecord(ev[k++], s));
+      ch->enqueue_halo(c, s);
     }
     ch->iters_done++;
   }
@@ -530,10 +614,10 @@ int bsb200_chain_state(bsb200_chain *ch, int32_t *z, double *weights, double *mu
   CK(cudaSetDevice(ch->device));
   cudaStream_t s = ch->stream;
   const int q = ch->q, d = ch->d;
-  if (z || weights) {
-    launch_snapshot(ch->z.p, ch->w.p, ch->orig.p, ch->n, ch->snap_z.p, ch->snap_w.p, s);
-    if (z) CK(cudaMemcpyAsync(z, ch->snap_z.p, sizeof(int32_t) * ch->n, cudaMemcpyDeviceToHost, s));
-    if (weights) CK(cudaMemcpyAsync(weights, ch->snap_w.p, sizeof(double) * ch->n, cudaMemcpyDeviceToHost, s));
+  if (z || weights) {   // own spots only; entries of other ranks are left untouched
+    launch_snapshot(ch->z.p, ch->w.p, ch->orig.p, ch->n_own, ch->snap_z.p, ch->snap_w.p, s, ch->lo);
+    if (z) CK(cudaMemcpyAsync(z + ch->lo, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
+    if (weights) CK(cudaMemcpyAsync(weights + ch->lo, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
   }
   std::vector<double> p((size_t) ch->PL.total);
   CK(cudaMemcpyAsync(p.data(), ch->params.p, sizeof(double) * p.size(), cudaMemcpyDeviceToHost, s));
@@ -556,14 +640,14 @@ int bsb200_chain_dry_sweep(bsb200_chain *ch, int32_t *z_new, double *w_new, doub
   if (!ch) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
   CK(cudaSetDevice(ch->device));
   cudaStream_t s = ch->stream;
-  const size_t n = (size_t) ch->n;
+  const size_t n = (size_t) ch->n;   // outputs are indexed by original spot id; own spots are filled
   DevBuf<int32_t> dz, da;
   DevBuf<double> dw, dhp, dhn, dpr;
   int rc;
   if ((rc = dz.alloc(n)) || (rc = da.alloc(n)) || (rc = dw.alloc(n)) || (rc = dhp.alloc(n)) || (rc = dhn.alloc(n)) || (rc = dpr.alloc(n))) return rc;
   // parameters of the next iteration are drawn first (k_param advances the iteration counter), the
   // dry sweep then evaluates that iteration's proposals on the unchanged labels / weights.
-  DevBuf<double> params_keep, plog_keep;
+  DevBuf<double> params_keep;
   if ((rc = params_keep.alloc((size_t) ch->PL.total))) return rc;
   CK(cudaMemcpyAsync(params_keep.p, ch->params.p, sizeof(double) * ch->PL.total, cudaMemcpyDeviceToDevice, s));
   ch->enqueue_reduce_and_param(false, s);
@@ -615,6 +699,8 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   out->rows_done = 1;
   out->ncolours = ch->ord.ncol;
   out->setup_ms = ch->setup_ms;
+  out->own_lo = ch->lo;
+  out->own_hi = ch->hi;
   double ms = 0.0;
   rc = chain_run_impl(ch, args->nrep - 1, out, &ms, true);
   out->device_ms = ms;

@@ -36,7 +36,9 @@ struct SpotOrder {
   std::vector<int32_t> seg_begin, seg_count, seg_slot;   // launch lists, colour-major
   std::vector<int32_t> colour_seg_start;                 // ncol + 1 offsets into the launch lists
   std::vector<int32_t> group_start;                      // ngroups + 1 offsets into the slots
-  int build(int64_t n, const int32_t *colour, int ncolours, int ngroups, int seg_spots);
+  // spots [lo, hi) = virtual shards [g0, g1) of ngroups_total; defaults: everything
+  int build(int64_t n, const int32_t *colour, int ncolours, int ngroups_total, int seg_spots, int g0 = 0, int g1 = -1,
+            int64_t lo = 0, int64_t hi = 0);
 };
 
 int select_device(int device);

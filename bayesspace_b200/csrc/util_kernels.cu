@@ -25,19 +25,19 @@ __global__ void __launch_bounds__(256) k_colmeans(const double *Y, int64_t n, do
 
 // Yp[c][i] = Y[c][orig[i]] - ybar[c]   (gather into internal order + centring)
 __global__ void k_permute_center(const double *Y, int64_t src_ld, int64_t count, int d, const int32_t *orig,
-                                 const double *ybar, double *Yp, int64_t dst_ld) {
+                                 const double *ybar, double *Yp, int64_t dst_ld, int64_t orig_off) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const int64_t o = orig[i];
+  const int64_t o = orig[i] - orig_off;
   for (int c = 0; c < d; c++) Yp[(size_t) c * dst_ld + i] = Y[(size_t) c * src_ld + o] - ybar[c];
 }
 
 // Snapshot of the labels / weights in the caller's spot order (src/cluster.cpp:313, :559-560).
 __global__ void k_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n,
-                           int32_t *z_out, double *w_out) {
+                           int32_t *z_out, double *w_out, int64_t orig_off) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t o = orig[i];
+  const int64_t o = orig[i] - orig_off;
   z_out[o] = (int32_t) z[i] + 1;
   if (w_out) w_out[o] = w[i];
 }
@@ -62,9 +62,20 @@ __global__ void k_running_mean(const double *snap, double *mean, int64_t len, do
 __global__ void k_reduce_groups(const double *partials, const int32_t *group_start, int E, double *gsum) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
   if (e >= E) return;
-  double s = 0.0;
-  for (int slot = group_start[g]; slot < group_start[g + 1]; slot++) s += partials[(size_t) slot * E + e];
-  gsum[(size_t) g * E + e] = s;
+  // four interleaved running sums (fixed association, independent of grid and GPU count) keep 8 loads in flight
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int slot = group_start[g];
+  const int end = group_start[g + 1];
+  const double *p = partials + (size_t) slot * E + e;
+#pragma unroll 2
+  for (; slot + 3 < end; slot += 4, p += 4 * (size_t) E) {
+    a0 += p[0];
+    a1 += p[E];
+    a2 += p[2 * (size_t) E];
+    a3 += p[3 * (size_t) E];
+  }
+  for (; slot < end; slot++, p += E) a0 += p[0];
+  gsum[(size_t) g * E + e] = (a0 + a1) + (a2 + a3);
 }
 
 // rooti / logdet per matrix for the log-density probe (one warp per matrix):
@@ -109,18 +120,64 @@ __global__ void k_scatter_probe(const double *stats, StatLayout SL, const double
   }
 }
 
+// Column sums of Y per virtual shard (rows [lo_g, hi_g) of a matrix with leading dimension ldy): one CTA per
+// (column, shard), 256 strided partial sums then a fixed tree.  The shard sums are folded in shard order on
+// the host, so the column means do not depend on how many GPUs share the chain.
+__global__ void __launch_bounds__(256) k_colsums_groups(const double *Y, int64_t ldy, const int64_t *group_lo,
+                                                       int64_t row_off, int d, double *gsums) {
+  __shared__ double red[256];
+  const int c = blockIdx.x, g = blockIdx.y;
+  const double *col = Y + (size_t) c * ldy - row_off;
+  double s = 0.0;
+  for (int64_t j = group_lo[g] + threadIdx.x; j < group_lo[g + 1]; j += 256) s += col[j];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gsums[(size_t) g * d + c] = red[0];
+}
+
+// Halo exchange of boundary labels: gather into / scatter from the contiguous NCCL buffers.
+__global__ void k_halo_pack(const uint8_t *z, const int32_t *pos, int count, uint8_t *buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) buf[i] = z[pos[i]];
+}
+__global__ void k_halo_unpack(uint8_t *z, const int32_t *pos, int count, const uint8_t *buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) z[pos[i]] = buf[i];
+}
+
+void launch_colsums_groups(const double *Y, int64_t ldy, const int64_t *group_lo, int64_t row_off, int d, int g_first,
+                           int g_count, double *gsums, cudaStream_t s) {
+  dim3 grid(d, g_count);
+  k_colsums_groups<<<grid, 256, 0, s>>>(Y, ldy, group_lo + g_first, row_off, d, gsums + (size_t) g_first * d);
+  g_launches++;
+}
+void launch_halo_pack(const uint8_t *z, const int32_t *pos, int count, uint8_t *buf, cudaStream_t s) {
+  if (count <= 0) return;
+  k_halo_pack<<<(count + 255) / 256, 256, 0, s>>>(z, pos, count, buf);
+  g_launches++;
+}
+void launch_halo_unpack(uint8_t *z, const int32_t *pos, int count, const uint8_t *buf, cudaStream_t s) {
+  if (count <= 0) return;
+  k_halo_unpack<<<(count + 255) / 256, 256, 0, s>>>(z, pos, count, buf);
+  g_launches++;
+}
+
 void launch_colmeans(const double *Y, int64_t n, int d, double *ybar, cudaStream_t s) {
   k_colmeans<<<d, 256, 0, s>>>(Y, n, ybar);
   g_launches++;
 }
 void launch_permute_center(const double *Y, int64_t src_ld, int64_t count, int d, const int32_t *orig,
-                           const double *ybar, double *Yp, int64_t dst_ld, cudaStream_t s) {
-  k_permute_center<<<(unsigned) ((count + 255) / 256), 256, 0, s>>>(Y, src_ld, count, d, orig, ybar, Yp, dst_ld);
+                           const double *ybar, double *Yp, int64_t dst_ld, cudaStream_t s, int64_t orig_off) {
+  k_permute_center<<<(unsigned) ((count + 255) / 256), 256, 0, s>>>(Y, src_ld, count, d, orig, ybar, Yp, dst_ld, orig_off);
   g_launches++;
 }
 void launch_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n, int32_t *z_out,
-                     double *w_out, cudaStream_t s) {
-  k_snapshot<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(z, w, orig, n, z_out, w_out);
+                     double *w_out, cudaStream_t s, int64_t orig_off) {
+  k_snapshot<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(z, w, orig, n, z_out, w_out, orig_off);
   g_launches++;
 }
 void launch_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, const int32_t *orig,
@@ -134,8 +191,8 @@ void launch_running_mean(const double *snap, double *mean, int64_t len, double i
 }
 void launch_reduce_groups(const double *partials, const int32_t *group_start, int ngroups, int E,
                           double *gsum, cudaStream_t s) {
-  dim3 grid((E + 127) / 128, ngroups);
-  k_reduce_groups<<<grid, 128, 0, s>>>(partials, group_start, E, gsum);
+  dim3 grid((E + 63) / 64, ngroups);
+  k_reduce_groups<<<grid, 64, 0, s>>>(partials, group_start, E, gsum);
   g_launches++;
 }
 void launch_factor(const double *mat, int nl, int d, int form, double *rooti, double *logdet, int *err,

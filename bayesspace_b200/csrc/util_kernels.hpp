@@ -10,9 +10,13 @@ namespace bsb {
 extern std::atomic<long long> g_launches;
 void launch_colmeans(const double *Y, int64_t n, int d, double *ybar, cudaStream_t s);
 void launch_permute_center(const double *Y, int64_t src_ld, int64_t count, int d, const int32_t *orig,
-                           const double *ybar, double *Yp, int64_t dst_ld, cudaStream_t s);
+                           const double *ybar, double *Yp, int64_t dst_ld, cudaStream_t s, int64_t orig_off = 0);
+void launch_colsums_groups(const double *Y, int64_t ldy, const int64_t *group_lo, int64_t row_off, int d, int g_first,
+                           int g_count, double *gsums, cudaStream_t s);
+void launch_halo_pack(const uint8_t *z, const int32_t *pos, int count, uint8_t *buf, cudaStream_t s);
+void launch_halo_unpack(uint8_t *z, const int32_t *pos, int count, const uint8_t *buf, cudaStream_t s);
 void launch_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n, int32_t *z_out,
-                     double *w_out, cudaStream_t s);
+                     double *w_out, cudaStream_t s, int64_t orig_off = 0);
 void launch_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, const int32_t *orig,
                        const double *ybar, double *out, int64_t dst_ld, cudaStream_t s);
 void launch_running_mean(const double *snap, double *mean, int64_t len, double inv_count, cudaStream_t s);

@@ -30,7 +30,7 @@ class _Keep(list):
 
 
 def _cluster_args(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, model, precision,
-                  seed, compat, device, colour, keep):
+                  seed, compat, device, colour, keep, groups=0, world=1, rank=0, comm_id=None):
     Y = np.asarray(Y, dtype=np.float64)
     if Y.shape != (n, d):
         raise _lib.BayesSpaceError(_lib.ERR_INVALID, "Dimensions of Y do not match n, d.")
@@ -56,14 +56,19 @@ def _cluster_args(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha
         col = i32(colour[0] if isinstance(colour, tuple) else colour)
         a.colour = keep.add(col)
         a.ncolours = int(colour[1]) if isinstance(colour, tuple) else int(col.max()) + 1
+    a.groups, a.world, a.rank = int(groups), int(world), int(rank)
+    if world > 1:
+        if comm_id is None or len(comm_id) != 128:
+            raise _lib.BayesSpaceError(_lib.ERR_INVALID, "world > 1 needs the 128-byte id of comm_unique_id()")
+        a.comm_id = keep.add(np.frombuffer(bytes(comm_id), dtype=np.uint8).copy())
     return a
 
 
 def _run_cluster(model, precision, Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta,
-                 seed=0, compat=COMPAT_REFERENCE, device=0, colour=None):
+                 seed=0, compat=COMPAT_REFERENCE, device=0, colour=None, groups=0, world=1, rank=0, comm_id=None):
     keep = _Keep()
     a = _cluster_args(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, model, precision,
-                      seed, compat, device, colour, keep)
+                      seed, compat, device, colour, keep, groups, world, rank, comm_id)
     nsnap = nrep // thin + 1
     nl = q if precision == "variable" else 1
     z = np.zeros((nsnap, n), dtype=np.int32)
@@ -78,8 +83,40 @@ def _run_cluster(model, precision, Y, df_j, nrep, thin, n, d, gamma, q, init, mu
     out = {"z": z, "mu": mu, "lambda": lam_m if nl > 1 else lam_m[:, 0], "plogLik": pl}
     if model == "t":
         out["weights"] = w
-    out["_info"] = {"ncolours": o.ncolours, "setup_ms": o.setup_ms, "device_ms": o.device_ms, "rows_done": o.rows_done}
+    out["_info"] = {"ncolours": o.ncolours, "setup_ms": o.setup_ms, "device_ms": o.device_ms, "rows_done": o.rows_done,
+                    "own": (int(o.own_lo), int(o.own_hi))}
     return out
+
+
+def comm_unique_id():
+    """128-byte communicator id (rank 0 calls this, every rank of a sharded chain receives the bytes)."""
+    buf = np.zeros(128, dtype=np.uint8)
+    check(lib().bsb200_comm_unique_id(ptr(buf)))
+    return bytes(buf)
+
+
+def shard_plan(df_j, colour, ncolours, groups, world, rank):
+    """Host-only view of one rank's share of a sharded chain: own range, ghost ids, halo lists (original ids)."""
+    p, idx = neighbors.as_csr(df_j)
+    n = len(p) - 1
+    col = i32(colour)
+    lo, hi, ng = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    L = lib()
+    check(L.bsb200_shard_plan(ptr(p), ptr(idx), C.c_int64(n), ptr(col), ncolours, groups, world, rank, C.byref(lo),
+                              C.byref(hi), None, C.c_int64(0), C.byref(ng), None, None, None))
+    ghosts = np.zeros(max(int(ng.value), 1), dtype=np.int32)
+    counts = np.zeros(2 * ncolours * world, dtype=np.int32)
+    check(L.bsb200_shard_plan(ptr(p), ptr(idx), C.c_int64(n), ptr(col), ncolours, groups, world, rank, C.byref(lo),
+                              C.byref(hi), ptr(ghosts), C.c_int64(len(ghosts)), C.byref(ng), ptr(counts), None, None))
+    K = ncolours * world
+    send_ids = np.zeros(max(int(counts[:K].sum()), 1), dtype=np.int32)
+    recv_ids = np.zeros(max(int(counts[K:].sum()), 1), dtype=np.int32)
+    check(L.bsb200_shard_plan(ptr(p), ptr(idx), C.c_int64(n), ptr(col), ncolours, groups, world, rank, C.byref(lo),
+                              C.byref(hi), ptr(ghosts), C.c_int64(len(ghosts)), C.byref(ng), ptr(counts), ptr(send_ids),
+                              ptr(recv_ids)))
+    return {"lo": int(lo.value), "hi": int(hi.value), "ghosts": ghosts[:int(ng.value)],
+            "send_counts": counts[:K].reshape(ncolours, world), "recv_counts": counts[K:].reshape(ncolours, world),
+            "send_ids": send_ids[:int(counts[:K].sum())], "recv_ids": recv_ids[:int(counts[K:].sum())]}
 
 
 def iterate(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, **kw):
@@ -172,10 +209,11 @@ class Chain:
     """A cluster sampler whose state stays resident in HBM between calls (bsb200_chain_*)."""
 
     def __init__(self, Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, model="t",
-                 precision="equal", seed=0, compat=COMPAT_REFERENCE, device=0, colour=None):
+                 precision="equal", seed=0, compat=COMPAT_REFERENCE, device=0, colour=None, groups=0, world=1, rank=0,
+                 comm_id=None):
         keep = _Keep()
         a = _cluster_args(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, model, precision,
-                          seed, compat, device, colour, keep)
+                          seed, compat, device, colour, keep, groups, world, rank, comm_id)
         self.n, self.d, self.q, self.nl, self.tdist = n, d, q, (q if precision == "variable" else 1), model == "t"
         self._h = C.c_void_p()
         check(lib().bsb200_chain_create(C.byref(a), C.byref(self._h)))

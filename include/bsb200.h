@@ -124,7 +124,12 @@ typedef struct bsb200_cluster_args {
   int32_t device;          /* CUDA device ordinal                                */
   const int32_t *colour;   /* optional n colours (0-based) from bsb200_colour_graph, or NULL */
   int32_t ncolours;
-  int32_t reserved;
+  int32_t groups;          /* virtual shards of the statistics fold: 0 = automatic (1, or 64 for n >= 262,144
+                              or world > 1); chains are bit-identical across GPU counts for equal `groups` */
+  /* spot sharding of ONE chain over `world` processes, one GPU each (every process passes the full inputs) */
+  int32_t world;           /* 0 or 1: single GPU */
+  int32_t rank;
+  const void *comm_id;     /* 128 bytes from bsb200_comm_unique_id() of rank 0, identical on all ranks */
 } bsb200_cluster_args;
 
 /* nsnap = nrep/thin + 1 rows.  Any pointer may be NULL to skip that output. */
@@ -138,9 +143,21 @@ typedef struct bsb200_cluster_out {
   int32_t ncolours;  /* out: colour classes used by the chromatic scan                  */
   double setup_ms;   /* out: host->device staging + graph setup, wall clock             */
   double device_ms;  /* out: device time of the sampling loop (CUDA events)             */
+  int64_t own_lo, own_hi; /* out: spots [own_lo, own_hi) of z / weights were written by this rank
+                             (all of them when world <= 1); mu / lambda / plogLik are complete on every rank */
 } bsb200_cluster_out;
 
 int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out);
+
+/* Multi-GPU (one process per GPU): rank 0 creates the communicator id, the host layer hands the 128 bytes to
+ * every rank (torch.distributed broadcast in bench.py), each rank passes them in bsb200_cluster_args.comm_id.
+ * Per iteration the ranks exchange the labels of boundary spots after every colour phase and allgather the
+ * per-shard statistics; there is no reference counterpart (the reference is single-process). */
+int bsb200_comm_unique_id(void *id128);
+/* Host-only view of a rank's share of a sharded chain (own range, ghost spots, halo lists); for tests. */
+int bsb200_shard_plan(const int64_t *ptr, const int32_t *idx, int64_t n, const int32_t *colour, int32_t ncolours,
+                      int32_t groups, int32_t world, int32_t rank, int64_t *lo, int64_t *hi, int32_t *ghosts,
+                      int64_t cap, int64_t *nghosts, int32_t *counts, int32_t *send_ids, int32_t *recv_ids);
 
 /* Resident-chain interface: the same sampler with state kept in HBM between calls.  bench.py uses
  * it to time sweeps with inputs already on the device; bsb200_cluster() is create + run + destroy. */
