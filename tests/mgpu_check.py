@@ -22,8 +22,6 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     rank, W = dist.get_rank(), dist.get_world_size()
-    ids = [samplers.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     cases = [("small_sq", (64, 64), "iterate", 16), ("small_hex", (60, 40), "iterate_t", 64),
              ("small_sq", (48, 64), "iterate_t_vvv", 8), ("small_hex", (40, 30), "iterate_vvv", 8)]
     for name, shape, fname, groups in cases:
@@ -32,6 +30,8 @@ def main():
         colour = B.colour_lattice(w.array_row, w.array_col, w.platform)
         args = (w.Y, csr, 24, 4, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0, w.alpha, w.beta)
         f = getattr(B, fname)
+        ids = [samplers.comm_unique_id() if rank == 0 else None]   # one communicator id per sharded chain
+        dist.broadcast_object_list(ids, src=0)
         alone = f(*args, seed=99, colour=colour, groups=groups, device=local)
         shard = f(*args, seed=99, colour=colour, groups=groups, device=local, world=W, rank=rank, comm_id=ids[0])
         lo, hi = shard["_info"]["own"]
