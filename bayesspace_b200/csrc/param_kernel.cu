@@ -1,10 +1,10 @@
 // param_kernel.cu -- k_param: the once-per-iteration "small" kernel of every sampler.
 //
-// One CTA.  (0) folds the per-segment statistics of the previous sweep in a fixed two-level order
-// (bit-reproducible, independent of grid size and GPU count) and closes plogLik of that sweep;
-// (1) draws mu_k | . for every cluster (one warp per cluster); (2) draws Lambda | . from the
-// Wishart (Bartlett) and factorises it ONCE for the whole sweep; (3) publishes the parameter
-// block (ParamLayout) the sweep CTAs stage into shared memory.
+// One CTA of 256 threads.  (0) folds the per-segment statistics of the previous sweep in a fixed two-level
+// order (bit-reproducible, independent of grid size and GPU count) and closes plogLik of that sweep;
+// (1) draws mu_k | . for every cluster; (2) draws Lambda | . from the Wishart (Bartlett) and factorises it
+// ONCE for the whole sweep; (3) publishes the parameter block (ParamLayout) the sweep CTAs stage into shared
+// memory.
 //
 // Reference steps replaced (file:line under /root/reference/src/cluster.cpp):
 //   mu update      :246-258  :359-372  :478-493  :609-625  :883-892
@@ -13,82 +13,192 @@
 //   plogLik[i] = sum(plogLikj) :307 :430 :553 :695, accu(log_likelihoods) :1056
 // RcppDist::rmvnorm / rwish semantics: SURVEY.md App. C.
 //
-// Linear algebra.  The reference forms inverses and then factorises them (inv(P) then chol inside
-// rmvnorm; inv(V+S) then chol inside rwish; inv(Lambda) then chol then inv inside dmvnrm_arma_fast).
+// Linear algebra.  The reference forms inverses and then factorises them (inv(P) then chol inside rmvnorm;
+// inv(V+S) then chol inside rwish; inv(Lambda) then chol then inv inside dmvnrm_arma_fast).
 // chol_upper(X^-1) is the inverse of the "reverse" Cholesky factor U of X (X = U U^T, U upper), and
-// inv(chol_upper(Lambda^-1)) is that factor of Lambda itself, so each of those chains is one
-// factorisation (+ one triangular inverse) here.  Same values up to rounding.
+// inv(chol_upper(Lambda^-1)) is that factor of Lambda itself, so each of those chains is one factorisation
+// (+ one triangular inverse) here.  Same values up to rounding.
+//
+// This kernel is pure latency (d <= 32): every d x d operation is spread over the whole CTA and over ALL
+// matrices of a phase at once (the q posterior precisions of the mu step; the q Wishart draws of the VVV
+// samplers), one thread per matrix element, so the critical path is d steps of one FMA + a barrier.
 #include "chain.hpp"
 #include "rng.cuh"
-#include "smallmat.cuh"
 
 namespace bsb {
+
+#define MAT(M, b, i, j) (M)[(b) * dd + (j) * d + (i)]
 
 __device__ __forceinline__ int pair_index(int a, int b, int d) {   // a <= b
   return a * d - a * (a - 1) / 2 + (b - a);
 }
 
-__device__ inline void pack_sym(const double *M, double *P, int d, int lane) {
-  for (int a = lane; a < d; a += 32)
-    for (int b = a; b < d; b++) P[pair_index(a, b, d)] = (a == b ? 1.0 : 2.0) * M[(size_t) b * d + a];
-  __syncwarp();
+#ifdef BSB_PARAM_TIMING
+__device__ long long g_param_clock[16];
+#define BSB_T(i) do { if (threadIdx.x == 0) g_param_clock[i] = clock64(); } while (0)
+#else
+#define BSB_T(i) do { } while (0)
+#endif
+
+// U (upper, U U^T = A) in place on nb matrices whose lower triangles are zero.  Right-looking from the
+// last column: scale column j by 1/sqrt(a_jj), then down-date the leading j x j block by its outer product.
+// Threads form a 32 x 8 grid (row = tid & 31, column / matrix = tid >> 5): no integer division on the
+// critical path.  Must be called by every thread of the CTA (256 threads).
+__device__ __forceinline__ void blk_revchol(int off_U, int nb, int d, int *ok) {
+  extern __shared__ double sm[];
+  double *U = sm + off_U;   // shared-memory window: keeps the accesses LDS/STS instead of generic LD/ST
+  const int dd = d * d;
+  const int ti = threadIdx.x & 31, tk = threadIdx.x >> 5;
+  for (int j = d - 1; j >= 0; j--) {
+    __syncthreads();
+    if (ti < j)
+      for (int b = tk; b < nb; b += 8) MAT(U, b, ti, j) *= rsqrt(MAT(U, b, j, j));
+    __syncthreads();
+    if (ti == 31) {   // the diagonal itself: nobody reads it any more in this step
+      for (int b = tk; b < nb; b += 8) {
+        const double s = MAT(U, b, j, j);
+        if (!(s > 0.0)) *ok = 0;
+        MAT(U, b, j, j) = sqrt(s);
+      }
+    } else {
+      for (int b = 0; b < nb; b++)
+        for (int k = tk; k < j; k += 8)
+          if (ti <= k) MAT(U, b, ti, k) -= MAT(U, b, ti, j) * MAT(U, b, k, j);
+    }
+  }
+  __syncthreads();
 }
 
-// g = M mu_k, c = mu_k^T g, gL = Lambda mu_k, cL = mu_k^T gL  (the expanded quadratic forms of the sweep)
-__device__ inline void derive_cluster_vectors(double *P, const ParamLayout &PL, const double *mu_s, const double *M,
-                                              const double *Lam, int k, double *v0, double *v1, int d, int lane) {
-  const double *muk = mu_s + k * d;
-  warp_matvec(M, muk, v0, d, lane);
-  warp_matvec(Lam, muk, v1, d, lane);
-  double s0 = 0.0, s1 = 0.0;
-  for (int c = lane; c < d; c += 32) {
-    P[PL.g + k * d + c] = v0[c];
-    P[PL.gL + k * d + c] = v1[c];
-    s0 += muk[c] * v0[c];
-    s1 += muk[c] * v1[c];
+// T = U^-1 for nb upper-triangular matrices, row by row from the bottom (T must not alias U).
+// rd: nb*d scratch for the reciprocals of the diagonals.
+__device__ __forceinline__ void blk_inv_upper(int off_U, int off_T, int off_rd, int nb, int d) {
+  extern __shared__ double sm[];
+  const double *U = sm + off_U;
+  double *T = sm + off_T, *rd = sm + off_rd;
+  const int dd = d * d;
+  const int ti = threadIdx.x & 31, tk = threadIdx.x >> 5;
+  if (ti < d)
+    for (int b = tk; b < nb; b += 8) rd[b * d + ti] = 1.0 / MAT(U, b, ti, ti);
+  __syncthreads();
+  for (int i = d - 1; i >= 0; i--) {
+    if (ti < d)
+      for (int b = tk; b < nb; b += 8) {
+        double v = 0.0;
+        if (ti >= i) {
+          double s = i == ti ? 1.0 : 0.0;
+          for (int k = i + 1; k <= ti; k++) s -= MAT(U, b, i, k) * MAT(T, b, k, ti);
+          v = s * rd[b * d + i];
+        }
+        MAT(T, b, i, ti) = v;
+      }
+    __syncthreads();
+  }
+}
+
+// ---- register-resident warp versions (one warp per matrix, lane k owns column k) ----------------------
+// The shared-memory versions above cost ~3,000 cycles per elimination step (dependent LDS -> DFMA -> STS
+// chains); with the column of every lane in registers a step is one rsqrt and j broadcasts (SHFL), which
+// makes these ~10x faster.  DM = d rounded up to 8, 16, 24 or 32; loops are fully unrolled so that every
+// register index is static, steps with j >= d are skipped (uniform predicate).
+template <int DM>
+__device__ __forceinline__ void warp_revchol_reg(double *U, int d, int lane, int *ok) {
+  double c[DM];
+#pragma unroll
+  for (int i = 0; i < DM; i++) c[i] = (lane < d && i <= lane) ? U[lane * d + i] : 0.0;
+#pragma unroll
+  for (int j = DM - 1; j >= 0; j--) {
+    if (j >= d) continue;
+    const double ajj = __shfl_sync(0xffffffffu, c[j], j);
+    if (!(ajj > 0.0)) *ok = 0;
+    const double r = rsqrt(ajj);
+    double ukj = 0.0;   // u_kj of this lane's own column k = lane
+#pragma unroll
+    for (int i = 0; i < j; i++) {
+      const double uij = __shfl_sync(0xffffffffu, c[i], j) * r;
+      if (i == lane) ukj = uij;
+    }
+#pragma unroll
+    for (int i = 0; i < j; i++) {
+      const double uij = __shfl_sync(0xffffffffu, c[i], j) * r;   // column j is still unscaled in lane j
+      if (lane < j && i <= lane) c[i] = fma(-uij, ukj, c[i]);
+    }
+    if (lane == j) {
+#pragma unroll
+      for (int i = 0; i < j; i++) c[i] *= r;
+      c[j] = ajj * r;
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-  }
-  if (lane == 0) {
-    P[PL.c + k] = s0;
-    P[PL.cL + k] = s1;
-  }
-  __syncwarp();
+  for (int i = 0; i < DM; i++)
+    if (lane < d && i < d) U[lane * d + i] = i <= lane ? c[i] : 0.0;
 }
 
-__global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem) {
+// T = U^-1 (upper), row by row from the bottom; U and T in shared memory (may not alias).
+template <int DM>
+__device__ __forceinline__ void warp_inv_upper_reg(const double *U, double *T, int d, int lane) {
+  double c[DM], t[DM];
+  double dg = 1.0;
+#pragma unroll
+  for (int i = 0; i < DM; i++) {
+    c[i] = (lane < d && i <= lane) ? U[lane * d + i] : 0.0;
+    t[i] = 0.0;
+    if (i == lane && lane < d) dg = c[i];
+  }
+  const double rdg = 1.0 / dg;
+#pragma unroll
+  for (int i = DM - 1; i >= 0; i--) {
+    if (i >= d) continue;
+    double s = lane == i ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = i + 1; k < DM; k++) {
+      if (k >= d) continue;
+      const double uik = __shfl_sync(0xffffffffu, c[i], k);   // U[i,k] lives in lane k
+      if (k <= lane) s = fma(-uik, t[k], s);
+    }
+    const double ri = __shfl_sync(0xffffffffu, rdg, i);
+    t[i] = lane >= i ? s * ri : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < DM; i++)
+    if (lane < d && i < d) T[lane * d + i] = i <= lane ? t[i] : 0.0;
+}
+
+template <int DM>
+__global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, int batch) {
   extern __shared__ double sm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
   const int d = a.PL.d, q = a.PL.q, nl = a.PL.nl, np = a.PL.np, E = a.SL.E;
-  const size_t dd = (size_t) d * d;
+  const int dd = d * d;
   const Key key{a.key0, a.key1};
   const uint32_t it_prev = *a.iter, it = it_prev + 1u;
   double *P = a.params;
   double *mu_s = sm;                                      // q*d   new means
-  double *eps_mu = mu_s + q * d;                          // q*d   N(0,1) draws of the mu update
-  double *wish = eps_mu + q * d;                          // np    Bartlett draws (shared precision only)
-  double *st = stats_in_smem ? wish + np : a.stats;       // reduced statistics
-  double *scr0 = wish + np + (stats_in_smem ? E : 0);
+  double *va = mu_s + q * d;                              // q*d   work vectors
+  double *vb = va + q * d;                                // q*d
+  double *st = stats_in_smem ? vb + q * d : a.stats;      // reduced statistics
+  double *MA = vb + q * d + (stats_in_smem ? E : 0);      // 4 work matrices per matrix of a batch
+  double *MB = MA + (size_t) batch * dd, *MC = MB + (size_t) batch * dd, *MD = MC + (size_t) batch * dd;
   const double LOG2PI = 1.8378770664093454835606594728112;
+  if (tid == 0) s_ok = 1;
+  BSB_T(0);
 
   // ---- (0) deterministic two-level reduction of the segment partials ---------------------------
-  for (int idx = tid; !a.gsum_ready && idx < E * a.ngroups; idx += blockDim.x) {
+  for (int idx = tid; !a.gsum_ready && idx < E * a.ngroups; idx += nt) {
     const int e = idx % E, g = idx / E;
     double s = 0.0;
     for (int slot = a.group_start[g]; slot < a.group_start[g + 1]; slot++) s += a.partials[(size_t) slot * E + e];
     a.gsum[(size_t) g * E + e] = s;
   }
   __syncthreads();
-  for (int e = tid; e < E; e += blockDim.x) {
+  for (int e = tid; e < E; e += nt) {
     double s = 0.0;
     for (int g = 0; g < a.ngroups; g++) s += a.gsum[(size_t) g * E + e];
     st[e] = s;
     if (stats_in_smem) a.stats[e] = s;
   }
   __syncthreads();
+  BSB_T(1);
 
   // plogLik of the sweep that just finished (uses the parameters of that sweep, still in P)
   if (it_prev >= 1u && warp == 0) {
@@ -111,155 +221,212 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem) {
   if (a.finalize_only) return;
   if (*a.err) return;
   __syncthreads();
-
-  // every variate of this iteration that does not depend on the statistics is drawn up front, one per
-  // thread (the transcendental chains of Box-Muller / Marsaglia-Tsang are long when run by a single warp)
-  for (int e = tid; e < q * d; e += blockDim.x) eps_mu[e] = rng_normal(key, P_MU, (uint32_t) (e / d), it, (uint32_t) (e % d));
-  if (nl == 1) {
-    const int df = (int) ((double) a.n + a.alpha);         // Q4: int df
-    for (int p = tid; p < np; p += blockDim.x) {
-      if (p < np - d) {
-        wish[d + p] = rng_normal(key, P_WISH_NORM, 0u, it, (uint32_t) p);   // A(i,j), i > j, index i(i-1)/2 + j
-      } else {
-        const int i = p - (np - d);
-        wish[i] = rng_gamma(key, P_WISH_CHI, (uint32_t) i, it, (df - i) / 2.0, 2.0);
-      }
-    }
-  }
-  __syncthreads();
-
-  double *scr = scr0 + (size_t) warp * (4 * dd + 4 * d);
-  double *A0 = scr, *A1 = A0 + dd, *A2 = A1 + dd, *A3 = A2 + dd;
-  double *v0 = A3 + dd, *v1 = v0 + d, *v2 = v1 + d, *v3 = v2 + d;
-  bool ok = true;
+  BSB_T(2);
 
   // ---- (1) mu_k ~ N(var (lambda0 mu0 + Lambda_k s_k), var), var = (lambda0 + n_k Lambda_k)^-1 ---
   // rmvnorm(1, mean, var) = eps chol(var) + mean with chol(var) = R = U^-1, lambda0 + n_k Lambda_k = U U^T,
-  // and mean = var rhs = R^T (R rhs):   mu_k = R^T (eps + R rhs).
-  for (int k = warp; k < q; k += nwarps) {
-    const double *Lk = P + a.PL.lam + (size_t) (a.vvv ? k : 0) * dd;
-    const double nk = st[a.SL.nk + k];
-    for (int e = lane; e < (int) dd; e += 32) {
-      const double l = Lk[e];
-      A3[e] = l;
-      A0[e] = a.lambda0[e] + nk * l;
+  // and mean = var rhs = R^T (R rhs):   mu_k = R^T (eps + R rhs).   All clusters of a batch at once.
+  for (int k0 = 0; k0 < q; k0 += batch) {
+    const int nb = min(batch, q - k0);
+    for (int idx = tid; idx < nb * (int) dd; idx += nt) {
+      const int b = idx / (int) dd, e = idx - b * (int) dd, i = e % d, j = e / d, k = k0 + b;
+      const double l = P[a.PL.lam + (size_t) (a.vvv ? k : 0) * dd + e];
+      MC[idx] = l;                                                                      // Lambda_k
+      MA[idx] = i <= j ? a.lambda0[e] + st[a.SL.nk + k] * l : 0.0;                      // upper triangle of P_k
     }
-    for (int c = lane; c < d; c += 32) v3[c] = st[a.SL.sk + k * d + c];
-    __syncwarp();
-    ok &= warp_revchol_upper(A0, A1, d, lane);     // A1 = U
-    warp_inv_upper(A1, A2, d, lane);               // A2 = R = chol_upper(var)
-    warp_matvec(A3, v3, v0, d, lane);              // v0 = Lambda_k s_k
-    for (int c = lane; c < d; c += 32) v0[c] += a.lm0[c];
-    __syncwarp();
-    warp_triu_matvec(A2, v0, v1, d, lane);         // v1 = R rhs
-    for (int c = lane; c < d; c += 32) v1[c] += eps_mu[k * d + c];
-    __syncwarp();
-    warp_triu_matvec_t(A2, v1, v2, d, lane);       // v2 = R^T (eps + R rhs)
-    for (int c = lane; c < d; c += 32) {
-      mu_s[k * d + c] = v2[c];
-      P[a.PL.mu + k * d + c] = v2[c];
+    __syncthreads();
+    if (DM <= 16) {
+      for (int b = warp; b < nb; b += 8) {
+        warp_revchol_reg<DM>(MA + b * dd, d, lane, &s_ok);            // MA = U
+        __syncwarp();
+        warp_inv_upper_reg<DM>(MA + b * dd, MB + b * dd, d, lane);    // MB = R = chol_upper(var)
+      }
+      __syncthreads();
+    } else {
+      blk_revchol((int) (MA - sm), nb, d, &s_ok);
+      blk_inv_upper((int) (MA - sm), (int) (MB - sm), (int) (va - sm), nb, d);
     }
-    __syncwarp();
+    for (int idx = tid; idx < nb * d; idx += nt) {   // va = lambda0 mu0 + Lambda_k s_k
+      const int b = idx / d, i = idx - b * d, k = k0 + b;
+      double s = a.lm0[i];
+      for (int j = 0; j < d; j++) s += MAT(MC, b, i, j) * st[a.SL.sk + k * d + j];
+      va[k * d + i] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * d; idx += nt) {   // vb = R rhs + eps
+      const int b = idx / d, i = idx - b * d, k = k0 + b;
+      double s = rng_normal(key, P_MU, (uint32_t) k, it, (uint32_t) i);
+      for (int j = i; j < d; j++) s += MAT(MB, b, i, j) * va[k * d + j];
+      vb[k * d + i] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * d; idx += nt) {   // mu = R^T vb
+      const int b = idx / d, j = idx - b * d, k = k0 + b;
+      double s = 0.0;
+      for (int i = 0; i <= j; i++) s += MAT(MB, b, i, j) * vb[k * d + i];
+      mu_s[k * d + j] = s;
+      P[a.PL.mu + k * d + j] = s;
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  BSB_T(3);
 
   // ---- (2) Lambda ~ Wishart(df, (beta I + S)^-1); factorise once for the sweep ------------------
-  for (int kk = warp; kk < nl; kk += nwarps) {
-    const double *T = a.SL.nlT ? st + a.SL.T + (size_t) (a.SL.nlT > 1 ? kk : 0) * np : a.T_fixed;
-    // V + S, S = sum_j w_j (y_j - mu_{z_j})(y_j - mu_{z_j})^T from the moment sums (upper triangle)
-    for (int e = lane; e < (int) dd; e += 32) {
-      const int ia = e % d, ib = e / d;
-      if (ia > ib) { A0[e] = 0.0; continue; }
-      double s = T[pair_index(ia, ib, d)];
-      const int k0 = a.vvv ? kk : 0, k1 = a.vvv ? kk + 1 : q;
-      for (int k = k0; k < k1; k++) {
-        const double ma = mu_s[k * d + ia], mb = mu_s[k * d + ib];
-        const double sa = st[a.SL.sk + k * d + ia], sb = st[a.SL.sk + k * d + ib];
-        s -= ma * sb + sa * mb - st[a.SL.nk + k] * ma * mb;
+  for (int k0 = 0; k0 < nl; k0 += batch) {
+    const int nb = min(batch, nl - k0);
+    for (int idx = tid; idx < nb * (int) dd; idx += nt) {
+      const int b = idx / (int) dd, e = idx - b * (int) dd, ia = e % d, ib = e / d, kk = k0 + b;
+      // V + S (upper triangle), S = sum_j w_j (y_j - mu_{z_j})(y_j - mu_{z_j})^T from the moment sums
+      double s = 0.0;
+      if (ia <= ib) {
+        const double *T = a.SL.nlT ? st + a.SL.T + (size_t) (a.SL.nlT > 1 ? kk : 0) * np : a.T_fixed;
+        s = T[pair_index(ia, ib, d)] + (ia == ib ? a.beta : 0.0);
+        const int c0 = a.vvv ? kk : 0, c1 = a.vvv ? kk + 1 : q;
+        for (int k = c0; k < c1; k++) {
+          const double ma = mu_s[k * d + ia], mb = mu_s[k * d + ib];
+          const double sa = st[a.SL.sk + k * d + ia], sb = st[a.SL.sk + k * d + ib];
+          s -= ma * sb + sa * mb - st[a.SL.nk + k] * ma * mb;
+        }
       }
-      A0[e] = s + (ia == ib ? a.beta : 0.0);
-    }
-    // Bartlett factor (lower triangular)
-    const int df = (int) ((a.vvv ? st[a.SL.cnt + kk] : (double) a.n) + a.alpha);   // Q4: int df
-    for (int e = lane; e < (int) dd; e += 32) {
-      const int i = e % d, j = e / d;
-      if (i <= j) A3[e] = 0.0;
-      else A3[e] = nl == 1 ? wish[d + i * (i - 1) / 2 + j]
-                           : rng_normal(key, P_WISH_NORM, (uint32_t) kk, it, (uint32_t) (i * (i - 1) / 2 + j));
-    }
-    __syncwarp();
-    for (int i = lane; i < d; i += 32) {
-      const double chi = nl == 1 ? wish[i]
-                                 : rng_gamma(key, P_WISH_CHI, (uint32_t) kk * 1024u + (uint32_t) i, it, (df - i) / 2.0, 2.0);
-      if (!(chi > 0.0)) ok = false;                // Q9: df - i <= 0 (empty cluster)
-      A3[(size_t) i * d + i] = sqrt(chi);
-    }
-    __syncwarp();
-    ok &= warp_revchol_upper(A0, A1, d, lane);     // V + S = U U^T
-    warp_inv_upper(A1, A2, d, lane);               // A2 = C = chol_upper((V + S)^-1)
-    // B = A^T C (upper triangular), Lambda = B^T B
-    for (int j = lane; j < d; j += 32)
-      for (int i = 0; i < d; i++) {
-        double s = 0.0;
-        for (int k = i; k <= j; k++) s += A3[(size_t) i * d + k] * A2[(size_t) j * d + k];
-        A0[(size_t) j * d + i] = s;
+      MA[idx] = s;
+      // Bartlett factor A (lower triangular): N(0,1) below the diagonal, sqrt(chi2(df - i)) on it
+      double av = 0.0;
+      if (ia > ib) {
+        av = rng_normal(key, P_WISH_NORM, (uint32_t) kk, it, (uint32_t) (ia * (ia - 1) / 2 + ib));
+      } else if (ia == ib) {
+        const int df = (int) ((a.vvv ? st[a.SL.cnt + kk] : (double) a.n) + a.alpha);   // Q4: int df
+        const double chi = rng_gamma(key, P_WISH_CHI, (uint32_t) kk * 1024u + (uint32_t) ia, it, (df - ia) / 2.0, 2.0);
+        if (!(chi > 0.0)) s_ok = 0;                // Q9: df - i <= 0 (empty cluster)
+        av = sqrt(chi);
       }
-    __syncwarp();
-    warp_ttt_tn(A0, A1, d, lane);                  // A1 = Lambda
-    double *Lnew = P + a.PL.lam + (size_t) kk * dd;
-    for (int e = lane; e < (int) dd; e += 32) Lnew[e] = A1[e];
-    pack_sym(A1, P + a.PL.PL + (size_t) kk * np, d, lane);
-    ok &= warp_revchol_upper(A1, A2, d, lane);     // Lambda = rooti rooti^T, rooti = inv(chol_upper(Sigma))
-    double ld = 0.0;
-    for (int i = 0; i < d; i++) ld += log(A2[(size_t) i * d + i]);
-    const double *M = A1;
-    if ((a.compat & BSB_COMPAT_Q1_BIT) && !a.precision_form) {
-      warp_ttt_tn(A2, A3, d, lane);                // quirk Q1: M = rooti^T rooti (dmvnrm_arma_fast, :96-100)
-      M = A3;
+      MC[idx] = av;
     }
-    pack_sym(M, P + a.PL.PM + (size_t) kk * np, d, lane);
-    if (lane == 0) P[a.PL.logdet + kk] = ld;
-    if (nl == 1) {   // shared precision: hand M / Lambda to the whole CTA (warp 0's scratch: A0 = M, A1 = Lambda)
-      if (M != A1) for (int e = lane; e < (int) dd; e += 32) A0[e] = A3[e];
-      else for (int e = lane; e < (int) dd; e += 32) A0[e] = A1[e];
-      __syncwarp();
+    __syncthreads();
+    if (DM <= 16) {
+      for (int b = warp; b < nb; b += 8) {
+        warp_revchol_reg<DM>(MA + b * dd, d, lane, &s_ok);            // V + S = U U^T
+        __syncwarp();
+        warp_inv_upper_reg<DM>(MA + b * dd, MB + b * dd, d, lane);    // MB = C = chol_upper((V + S)^-1)
+      }
+      __syncthreads();
     } else {
-      derive_cluster_vectors(P, a.PL, mu_s, M, A1, kk, v0, v1, d, lane);
+      blk_revchol((int) (MA - sm), nb, d, &s_ok);
+      blk_inv_upper((int) (MA - sm), (int) (MB - sm), (int) (va - sm), nb, d);
     }
+    for (int idx = tid; idx < nb * (int) dd; idx += nt) {   // MD = B = A^T C (upper triangular)
+      const int b = idx / (int) dd, e = idx - b * (int) dd, i = e % d, j = e / d;
+      double s = 0.0;
+      for (int k = i; k <= j; k++) s += MAT(MC, b, k, i) * MAT(MB, b, k, j);
+      MD[idx] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * (int) dd; idx += nt) {   // Lambda = B^T B -> MB (full), MA (upper triangle)
+      const int b = idx / (int) dd, e = idx - b * (int) dd, i = e % d, j = e / d, kk = k0 + b;
+      const int k1 = i < j ? i : j;
+      double s = 0.0;
+      for (int k = 0; k <= k1; k++) s += MAT(MD, b, k, i) * MAT(MD, b, k, j);
+      P[a.PL.lam + (size_t) kk * dd + e] = s;
+      if (i <= j) P[a.PL.PL + (size_t) kk * np + pair_index(i, j, d)] = (i == j ? 1.0 : 2.0) * s;
+      MC[idx] = s;
+      MA[idx] = i <= j ? s : 0.0;
+    }
+    __syncthreads();
+    if (DM <= 16) {
+      for (int b = warp; b < nb; b += 8) warp_revchol_reg<DM>(MA + b * dd, d, lane, &s_ok);   // Lambda = rooti rooti^T
+      __syncthreads();
+    } else {
+      blk_revchol((int) (MA - sm), nb, d, &s_ok);
+    }
+    const bool q1 = (a.compat & BSB_COMPAT_Q1_BIT) && !a.precision_form;
+    for (int idx = tid; idx < nb * (int) dd; idx += nt) {   // density matrix M -> MD and packed into P
+      const int b = idx / (int) dd, e = idx - b * (int) dd, i = e % d, j = e / d, kk = k0 + b;
+      double s;
+      if (q1) {   // quirk Q1: M = rooti^T rooti (dmvnrm_arma_fast multiplies rooti * x, :96-100)
+        const int k1 = i < j ? i : j;
+        s = 0.0;
+        for (int k = 0; k <= k1; k++) s += MAT(MA, b, k, i) * MAT(MA, b, k, j);
+      } else {
+        s = MC[idx];
+      }
+      MD[idx] = s;
+      if (i <= j) P[a.PL.PM + (size_t) kk * np + pair_index(i, j, d)] = (i == j ? 1.0 : 2.0) * s;
+    }
+    for (int b = warp; b < nb; b += 8) {           // log-determinant term: sum log diag(rooti)
+      double ld = lane < d ? log(MAT(MA, b, lane, lane)) : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+      if (lane == 0) P[a.PL.logdet + k0 + b] = ld;
+    }
+    __syncthreads();
+    // derived per-cluster vectors: g = M mu, gL = Lambda mu (then c = mu^T g, cL = mu^T gL)
+    const int c0 = a.vvv ? k0 : 0, c1 = a.vvv ? k0 + nb : q;
+    for (int idx = tid; idx < (c1 - c0) * d; idx += nt) {
+      const int k = c0 + idx / d, i = idx % d, b = a.vvv ? k - k0 : 0;
+      double s0 = 0.0, s1 = 0.0;
+      for (int j = 0; j < d; j++) {
+        const double m = mu_s[k * d + j];
+        s0 += MAT(MD, b, i, j) * m;
+        s1 += MAT(MC, b, i, j) * m;
+      }
+      va[k * d + i] = s0;
+      vb[k * d + i] = s1;
+      P[a.PL.g + k * d + i] = s0;
+      P[a.PL.gL + k * d + i] = s1;
+    }
+    __syncthreads();
+    for (int k = c0 + tid; k < c1; k += nt) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int i = 0; i < d; i++) { s0 += mu_s[k * d + i] * va[k * d + i]; s1 += mu_s[k * d + i] * vb[k * d + i]; }
+      P[a.PL.c + k] = s0;
+      P[a.PL.cL + k] = s1;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (nl == 1)   // derived vectors of every cluster, one warp per cluster
-    for (int k = warp; k < q; k += nwarps) derive_cluster_vectors(P, a.PL, mu_s, scr0, scr0 + dd, k, v0, v1, d, lane);
-  if (!ok) atomicExch(a.err, BSB_DEVERR_NUMERIC);
-  __syncthreads();
+  BSB_T(4);
+  if (tid == 0 && !s_ok) atomicExch(a.err, BSB_DEVERR_NUMERIC);
 
   // ---- (3) snapshots of mu / Lambda at thin boundaries (:309-314) and iteration counter ---------
   if ((it + 1u) % (uint32_t) a.thin == 0u) {
     const size_t r = (it + 1u) / (uint32_t) a.thin;
     if (r <= (size_t) (a.nrep / a.thin)) {
       if (a.snap_mu)
-        for (int e = tid; e < q * d; e += blockDim.x) a.snap_mu[r * q * d + e] = mu_s[e] + a.ybar[e % d];
+        for (int e = tid; e < q * d; e += nt) a.snap_mu[r * q * d + e] = mu_s[e] + a.ybar[e % d];
       if (a.snap_lambda)
-        for (int e = tid; e < nl * (int) dd; e += blockDim.x) a.snap_lambda[r * nl * dd + e] = P[a.PL.lam + e];
+        for (int e = tid; e < nl * (int) dd; e += nt) a.snap_lambda[r * nl * dd + e] = P[a.PL.lam + e];
     }
   }
   if (tid == 0) *a.iter = it;
+  BSB_T(5);
 }
 
 static const size_t kParamSmemMax = 220 * 1024;
 
 void launch_param(const ParamArgs &a, cudaStream_t stream) {
   const int d = a.PL.d, q = a.PL.q;
-  int nwarps = d <= 16 ? 8 : 4;
-  const size_t per_warp = (4 * (size_t) d * d + 4 * d) * sizeof(double);
-  const size_t base = (2 * (size_t) q * d + a.PL.np) * sizeof(double), stats_bytes = (size_t) a.SL.E * sizeof(double);
-  const int stats_in_smem = base + stats_bytes + nwarps * per_warp <= kParamSmemMax;
-  const size_t smem = base + (stats_in_smem ? stats_bytes : 0) + nwarps * per_warp;
-  k_param<<<1, nwarps * 32, smem, stream>>>(a, stats_in_smem);
+  const size_t per_mat = 4 * (size_t) d * d * sizeof(double);
+  const size_t base = 3 * (size_t) q * d * sizeof(double), stats_bytes = (size_t) a.SL.E * sizeof(double);
+  const int want = q;   // matrices of the largest phase
+  int stats_in_smem = base + stats_bytes + per_mat <= kParamSmemMax && stats_bytes <= 96 * 1024;
+  size_t avail = kParamSmemMax - base - (stats_in_smem ? stats_bytes : 0);
+  int batch = (int) std::min<size_t>((size_t) want, avail / per_mat);
+  if (batch < 1) batch = 1;
+  const size_t smem = base + (stats_in_smem ? stats_bytes : 0) + (size_t) batch * per_mat;
+  // d <= 16: factorisations with one register-resident column per lane; larger d: shared-memory versions
+  if (d <= 8) k_param<8><<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
+  else if (d <= 16) k_param<16><<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
+  else k_param<32><<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
 }
 
+#ifdef BSB_PARAM_TIMING
+extern "C" int bsb200_debug_param_timing(long long *out16) {
+  return (int) cudaMemcpyFromSymbol(out16, g_param_clock, sizeof(long long) * 16);
+}
+#endif
+
 void param_kernel_init() {
-  cudaFuncSetAttribute(k_param, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
+  cudaFuncSetAttribute(k_param<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
+  cudaFuncSetAttribute(k_param<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
+  cudaFuncSetAttribute(k_param<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
 }
 
 }   // namespace bsb

@@ -9,8 +9,11 @@ metric -- is defined.  C2 (Visium, 4,992 spots) and C4 (700k bins) are reported 
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c2] [--impl reference]
 
-N > 1 is launched by the driver through torch.distributed.run; ranks run one independent chain each
-(the qTune / multi-chain mode of the north_star: no data-path collective, "scaling": "weak").
+N > 1 is launched by the driver through torch.distributed.run, one rank per GPU: ONE chain is spot-sharded over
+the N GPUs in row strips (labels of boundary spots exchanged after every colour phase, per-shard statistics
+allgathered once per iteration, both on NCCL inside the captured graph): total work fixed, "scaling": "strong".
+The sharded chain is bit-identical to the 1-GPU chain (tests/mgpu_check.py).  `--replicas` runs one independent
+chain per GPU instead (the qTune / multi-chain mode: no data-path collective, weak scaling).
 """
 import argparse
 import json
@@ -221,8 +224,9 @@ def run_gpu(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")   # plumbing only (ids, barriers, max of the timings); data path = library's NCCL
     import bayesspace_b200 as B
+    from bayesspace_b200 import samplers
     if B.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; bayesspace_b200 has no CPU fallback")
     K, W = max(1, args.steps), max(3, args.warmup)
@@ -233,8 +237,18 @@ def run_gpu(args):
 
     thin = 100
     nrep = W + 2 * K + 64
-    ch = B.Chain(*chain_args(w, csr, nrep, thin), model=w.model, precision=w.precision, seed=149 + rank,
-                 device=local, colour=colour)
+    sharded = world > 1 and not args.replicas
+
+    def comm_id():
+        if not sharded:
+            return None
+        ids = [samplers.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+
+    shard_kw = dict(world=world, rank=rank, comm_id=comm_id()) if sharded else {}
+    ch = B.Chain(*chain_args(w, csr, nrep, thin), model=w.model, precision=w.precision,
+                 seed=149 + (0 if sharded else rank), device=local, colour=colour, **shard_kw)
     ch.run(W)
     clocks = ClockSampler(local)
     if dist:
@@ -248,27 +262,46 @@ def run_gpu(args):
     if dist:
         import torch
         torch.cuda.synchronize()
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
     prof = ch.profile(min(K, 50))
     ck = clocks.stop()
     ch.close()
+    # ---- end to end through the C ABI with host buffers (bsb200_cluster: H2D, chain, snapshots D2H) ------
+    e2e_iters = args.e2e_iters
+    if dist:
+        dist.barrier()
+    e2e_kw = dict(world=world, rank=rank, comm_id=comm_id()) if sharded else {}
+    t0 = time.perf_counter()
+    out = B.cluster(w.Y, w.q, csr, init=w.init, model=w.model, precision=w.precision, mu0=w.mu0, lambda0=w.lambda0,
+                    gamma=w.gamma, alpha=w.alpha, beta=w.beta, nrep=e2e_iters + 1, thin=100, seed=7, device=local,
+                    colour=colour, **e2e_kw)
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
-    value = world * w.n * K / (ms * 1e-3)
+    total_units = w.n if sharded or world == 1 else world * w.n
+    n_dev = w.n // world if sharded else w.n          # spot-updates one GPU does per sweep
+    value = total_units * K / (ms * 1e-3)
     sweep_ms_per_launch = prof["sweep_ms"] / max(1, prof["sweep_launches"])
-    bytes_per_launch = Bspot * w.n / colour[1]
+    bytes_per_launch = Bspot * n_dev / colour[1]
     achieved = bytes_per_launch / (sweep_ms_per_launch * 1e-3) / 1e9
     line = {"metric": "spot-updates/s", "value": value, "unit": "spot-updates/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak" if (world > 1 and not sharded) else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(w, args.workload, parallelism="1 chain per GPU (replicas, no collective)"
-                                      if world > 1 else "single chain, 1 GPU",
-                                      sweeps_per_s=world * K / (ms * 1e-3), colours=colour[1]),
+            "config": workload_config(w, args.workload, parallelism=(
+                "one chain spot-sharded over %d GPUs in row strips (halo labels + allgather of shard statistics on NCCL)"
+                % world if sharded else ("1 chain per GPU (replicas, no collective)" if world > 1 else "single chain, 1 GPU")),
+                sweeps_per_s=(1 if sharded or world == 1 else world) * K / (ms * 1e-3), colours=colour[1]),
             "roofline": {"bound": "hbm", "kernel": "k_sweep<%d,t,shared>" % w.d, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(args.workload),
                          "traffic_source": "profiles/r1_sweep_%s_ncu.json (ncu --set full, bytes per launch)" % args.workload,
@@ -276,24 +309,17 @@ def run_gpu(args):
                          "avg_launch_ms": sweep_ms_per_launch, "formula": ALGO_NOTE,
                          "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50))},
             "gpu_launches": int(launches), "clocks": ck}
-    # ---- end to end through the C ABI with host buffers (bsb200_cluster: H2D, chain, snapshots D2H) ------
-    e2e_iters = args.e2e_iters
-    t0 = time.perf_counter()
-    out = B.cluster(w.Y, w.q, csr, init=w.init, model=w.model, precision=w.precision, mu0=w.mu0, lambda0=w.lambda0,
-                    gamma=w.gamma, alpha=w.alpha, beta=w.beta, nrep=e2e_iters + 1, thin=100, seed=7, device=local,
-                    colour=colour)
-    e2e_s = time.perf_counter() - t0
     nsnap = (e2e_iters + 1) // 100
     h2d = w.n * w.d * 8 + w.n * 4 + len(csr[1]) * 4 + (w.n + 1) * 8
     d2h = nsnap * w.n * (4 + (8 if w.model == "t" else 0)) + (e2e_iters + 1) * 8
-    line["e2e"] = {"value": world * w.n * e2e_iters / e2e_s, "unit": "spot-updates/s",
+    line["e2e"] = {"value": total_units * e2e_iters / e2e_s, "unit": "spot-updates/s",
                    "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
                    "call": "bsb200_cluster(nrep=%d, thin=100) with host buffers: wall clock of the whole call "
                            "(host-side graph colouring/ordering, H2D, %d sweeps, %d snapshots D2H)" %
                            (e2e_iters + 1, e2e_iters, nsnap),
                    "wall_s": e2e_s, "setup_ms": out["_info"]["setup_ms"], "device_ms": out["_info"]["device_ms"]}
     # ---- CPU baseline beside it (rank 0, bounded sample) ----------------------------------------------------
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         cb, _ = cpu_baseline(w, csr)
         line["cpu_baseline"] = cb
     # ---- the other sizes the metric is quoted on -------------------------------------------------------------
@@ -325,6 +351,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=["c5", "c4", "c2"])
     ap.add_argument("--e2e-iters", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: one independent chain per GPU instead of sharding")
     ap.add_argument("--no-others", dest="others", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
