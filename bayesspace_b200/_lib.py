@@ -100,8 +100,11 @@ def f64(a):
 
 
 def colmajor(a):
-    """2-D array -> flat float64 buffer in R's column-major layout."""
-    return np.asfortranarray(np.asarray(a, dtype=np.float64)).ravel(order="F")
+    """2-D array -> flat float64 buffer in R's column-major layout (a view when `a` already is F-ordered)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2 and a.flags.f_contiguous:
+        return a.reshape(-1, order="F")
+    return np.asfortranarray(a).ravel(order="F")
 
 
 def i32(a):

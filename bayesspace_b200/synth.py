@@ -54,7 +54,7 @@ def make_pcs(truth, d, q, rng, tdist=False):
             eps /= np.sqrt(w)[:, None]
         Y[s:e] = mu[truth[s:e] - 1] + eps
     Y -= Y.mean(axis=0)
-    return Y, mu, Sigma
+    return np.asfortranarray(Y), mu, Sigma   # column-major like an R matrix: the C ABI takes it without a copy
 
 
 def noisy_init(truth, q, rng, frac=0.2):

@@ -215,6 +215,39 @@ def time_workload(B, w, csr, colour, K, W, device, with_profile=True):
     return ms, launches, prof, setup_s
 
 
+def deconv_workload(B, device, peak, with_cpu):
+    """BASELINE config C3: iterate_deconv on the Visium lattice (4,992 parents x 6 subspots, t model)."""
+    from bayesspace_b200 import synth
+    w, csr, _ = build_workload("c2")
+    pos = np.c_[w.array_col.astype(float), w.array_row * np.sqrt(3.0)]
+    dc = synth.deconv_inputs(w.Y, pos, 1.0, np.sqrt(3.0), w.truth, platform="Visium", jitter_prior=0.3)
+    args = lambda nrep: (dc["positions2"], dc["dist"], csr, dc["Y2"], True, nrep, 100, dc["n"], dc["n0"], w.d, 2.0, w.q,
+                         dc["init1"], dc["subspots"], False, 5.0, 0, dc["c"], w.mu0, w.lambda0, w.alpha, w.beta, 1)
+    B.iterate_deconv(*args(101), seed=3, device=device, keep_Y=False)            # warm-up (graph, caches)
+    iters = 2000
+    out = B.iterate_deconv(*args(iters + 1), seed=3, device=device, keep_Y=False, mean_from=1)
+    ms = out["_info"]["device_ms"]
+    bytes_per = 16.0 * w.d + 8.0 * w.d / dc["subspots"] + 8 + 4 * 3 + 16
+    res = {"config": {"workload": "C3: iterate_deconv, 4,992 Visium spots x 6 subspots = 29,952 subspots, t model, q=7, "
+                                  "d=15, jitter.scale=5 (fixed proposal)", "n_subspots": dc["n"]},
+           "subspot_updates_per_s": dc["n"] * iters / (ms * 1e-3), "sweeps_per_s": iters / (ms * 1e-3),
+           "us_per_iteration": 1e3 * ms / iters, "Ychange_mean": float(np.nanmean(out["Ychange"])),
+           "hbm_frac_whole_iteration": bytes_per * dc["n"] * iters / (ms * 1e-3) / 1e9 / peak}
+    if with_cpu:
+        from oracle import oracle as O
+        strings = synth.neighbor_strings(*csr)
+        for threads in (1, 8):
+            a = list(args(4))
+            a[2] = strings
+            a[-1] = threads
+            t0 = time.perf_counter()
+            O.iterate_deconv(*a, seed=3, keep_Y=False)
+            t = time.perf_counter() - t0
+            res["cpu_baseline_%dthread" % threads] = {"value": dc["n"] * 3 / t, "unit": "subspot-updates/s", "cores": threads,
+                                                      "kind": "port", "sample": "3 sweeps of the same workload, %.1f s" % t}
+    return res
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -336,6 +369,7 @@ def run_gpu(args):
                             "hbm_frac_sweep_kernel": (b2 * w2.n / col2[1]) / (per_launch * 1e-3) / 1e9 / peak}
             if not args.no_cpu:
                 others[name]["cpu_baseline"], _ = cpu_baseline(w2, csr2, budget_s=8.0)
+        others["c3"] = deconv_workload(B, local, peak, not args.no_cpu)
         line["other_workloads"] = others
     print(json.dumps(line), flush=True)
     if dist:
