@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -109,8 +110,10 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
 
 int choose_groups(int64_t n) { return n >= 262144 ? kGroups : 1; }
 int choose_segment(int64_t n) {
+  // tiles per segment: a function of n only (the fold order, hence the bits of a chain, depends on it)
   int64_t tps = n / ((int64_t) kBlock * 2048);
-  tps = std::max<int64_t>(1, std::min<int64_t>(16, tps));
+  tps = std::max<int64_t>(1, std::min<int64_t>(8, tps));
+  if (const char *e = getenv("BSB200_SEG_TILES")) tps = std::max(1, atoi(e));   // tuning knob
   return (int) tps * kBlock;
 }
 

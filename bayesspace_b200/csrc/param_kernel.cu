@@ -192,8 +192,18 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
   }
   __syncthreads();
   for (int e = tid; e < E; e += nt) {
+    // shard sums folded in shard order (fixed association); loads issued 8 at a time ahead of the adds
+    const double *gp = a.gsum + e;
     double s = 0.0;
-    for (int g = 0; g < a.ngroups; g++) s += a.gsum[(size_t) g * E + e];
+    int g = 0;
+    for (; g + 8 <= a.ngroups; g += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldcg(gp + (size_t) (g + u) * E);
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += v[u];
+    }
+    for (; g < a.ngroups; g++) s += __ldcg(gp + (size_t) g * E);
     st[e] = s;
     if (stats_in_smem) a.stats[e] = s;
   }

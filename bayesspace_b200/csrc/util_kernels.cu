@@ -59,23 +59,36 @@ __global__ void k_running_mean(const double *snap, double *mean, int64_t len, do
 
 // Level 1 of the two-level statistics reduction when there are many segments: one thread per
 // (group, entry), sequential over the group's slots (fixed order).
-__global__ void k_reduce_groups(const double *partials, const int32_t *group_start, int E, double *gsum) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
-  if (e >= E) return;
-  // four interleaved running sums (fixed association, independent of grid and GPU count) keep 8 loads in flight
+__global__ void __launch_bounds__(256) k_reduce_groups(const double *partials, const int32_t *group_start, int E,
+                                                      double *gsum) {
+  // CTA = 32 entries x 8 sub-ranges of the group's slots.  Each thread folds its sub-range with four interleaved
+  // running sums, the 8 sub-range sums are then folded in order: a fixed association that depends only on the
+  // group's slot count (a global quantity), never on the grid or the GPU count.
+  __shared__ double sub[8][33];
+  const int le = threadIdx.x & 31, sr = threadIdx.x >> 5, e = blockIdx.x * 32 + le, g = blockIdx.y;
+  const int begin = group_start[g], end = group_start[g + 1];
+  const int len = (end - begin + 7) / 8;
+  int slot = begin + sr * len;
+  const int stop = min(end, slot + len);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int slot = group_start[g];
-  const int end = group_start[g + 1];
-  const double *p = partials + (size_t) slot * E + e;
-#pragma unroll 2
-  for (; slot + 3 < end; slot += 4, p += 4 * (size_t) E) {
-    a0 += p[0];
-    a1 += p[E];
-    a2 += p[2 * (size_t) E];
-    a3 += p[3 * (size_t) E];
+  if (e < E) {
+    const double *p = partials + (size_t) slot * E + e;
+    for (; slot + 3 < stop; slot += 4, p += 4 * (size_t) E) {
+      a0 += __ldcg(p);
+      a1 += __ldcg(p + E);
+      a2 += __ldcg(p + 2 * (size_t) E);
+      a3 += __ldcg(p + 3 * (size_t) E);
+    }
+    for (; slot < stop; slot++, p += E) a0 += __ldcg(p);
   }
-  for (; slot < end; slot++, p += E) a0 += p[0];
-  gsum[(size_t) g * E + e] = (a0 + a1) + (a2 + a3);
+  sub[sr][le] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (sr == 0 && e < E) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) s += sub[r][le];
+    gsum[(size_t) g * E + e] = s;
+  }
 }
 
 // rooti / logdet per matrix for the log-density probe (one warp per matrix):
@@ -191,8 +204,8 @@ void launch_running_mean(const double *snap, double *mean, int64_t len, double i
 }
 void launch_reduce_groups(const double *partials, const int32_t *group_start, int ngroups, int E,
                           double *gsum, cudaStream_t s) {
-  dim3 grid((E + 63) / 64, ngroups);
-  k_reduce_groups<<<grid, 64, 0, s>>>(partials, group_start, E, gsum);
+  dim3 grid((E + 31) / 32, ngroups);
+  k_reduce_groups<<<grid, 256, 0, s>>>(partials, group_start, E, gsum);
   g_launches++;
 }
 void launch_factor(const double *mat, int nl, int d, int form, double *rooti, double *logdet, int *err,

@@ -254,6 +254,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout and would precede the JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
