@@ -160,8 +160,11 @@ struct bsb200_chain {
   int kernels_per_iter = 0;
   double setup_ms = 0;
   int comm_rc = 0;               // first NCCL failure seen while enqueuing (reported by the next sync point)
+  double *gsum_p = nullptr;      // shard sums: own buffer, or the exported window of the peer transport
 
   ~bsb200_chain() {
+    if (stream) cudaStreamSynchronize(stream);
+    comm.shutdown();               // unmap the peers before the exported label array goes away
     if (graph_iter) cudaGraphExecDestroy(graph_iter);
     if (graph_batch) cudaGraphExecDestroy(graph_batch);
     if (ev0) cudaEventDestroy(ev0);
@@ -189,7 +192,8 @@ struct bsb200_chain {
   ParamArgs param_args(bool finalize_only) const {
     ParamArgs a{};
     a.PL = PL; a.SL = SL; a.params = params.p; a.partials = partials.p; a.group_start = group_start.p;
-    a.ngroups = G; a.gsum = gsum.p; a.gsum_ready = G > 1; a.stats = stats.p;
+    a.ngroups = G; a.gsum = gsum_p; a.gsum_ready = G > 1; a.stats = stats.p;
+    if (comm.peer()) { a.gepoch = comm.gather_epoch(); a.gsum_stride = comm.gsum_stride; }
     a.T_fixed = T_fixed.p; a.mu0c = mu0c.p; a.lambda0 = lambda0.p; a.lm0 = lm0.p; a.ybar = ybar.p;
     a.alpha = alpha; a.beta = beta; a.n = n; a.tdist = tdist; a.vvv = vvv; a.compat = compat;
     a.key0 = (uint32_t) seed; a.key1 = (uint32_t) (seed >> 32);
@@ -201,9 +205,13 @@ struct bsb200_chain {
   // level 1 of the statistics fold on the shards this rank owns, allgather of the shard sums, k_param
   void enqueue_reduce_and_param(bool finalize_only, cudaStream_t s) {
     if (G > 1) {
-      launch_reduce_groups(partials.p, group_start.p, ord.ngroups, SL.E, gsum.p + (size_t) plan.g0 * SL.E, s);
-      if (world() > 1) {
-        int rc = comm.allgather_f64(gsum.p, (size_t) ord.ngroups * SL.E, s);
+      const bool peer = comm.peer();
+      launch_reduce_groups(partials.p, group_start.p, ord.ngroups, SL.E, gsum_p + (size_t) plan.g0 * SL.E, s,
+                           peer ? comm.gather_epoch() : nullptr, comm.gsum_stride);
+      if (peer) {
+        comm.enqueue_gather_peer((size_t) plan.g0 * SL.E, (size_t) ord.ngroups * SL.E, err.p, s);
+      } else if (world() > 1) {
+        int rc = comm.allgather_f64(gsum_p, (size_t) ord.ngroups * SL.E, s);
         if (rc && !comm_rc) comm_rc = rc;
       }
     }
@@ -219,6 +227,10 @@ struct bsb200_chain {
   // labels of the boundary spots of one colour travel to the ranks that hold them as ghosts
   void enqueue_halo(int colour, cudaStream_t s) {
     if (world() <= 1) return;
+    if (comm.peer()) {
+      comm.enqueue_halo_peer(colour, z.p, send_pos.p, err.p, s);
+      return;
+    }
     const int W = world();
     const int32_t *so = halo.send_off.data() + (size_t) colour * W, *ro = halo.recv_off.data() + (size_t) colour * W;
     const int ns = so[W] - so[0], nr = ro[W] - ro[0];
@@ -262,6 +274,9 @@ static int check_device_error(bsb200_chain *ch) {
   CK(cudaMemcpyAsync(&e, ch->err.p, sizeof(int), cudaMemcpyDeviceToHost, ch->stream));
   CK(cudaStreamSynchronize(ch->stream));
   if (ch->comm_rc) return ch->comm_rc;
+  if (e == BSB_DEVERR_PEER_TIMEOUT)
+    return fail(BSB200_ERR_CUDA, "a peer rank did not answer within %.0f s (lost rank, or ranks running different calls)",
+                1e-9 * (double) BSB_PEER_TIMEOUT_NS);
   if (e == BSB_DEVERR_NUMERIC)
     return fail(BSB200_ERR_NUMERIC, "NA in probability vector, empty cluster (Wishart df <= 0) or matrix not positive definite");
   return BSB200_OK;
@@ -290,6 +305,15 @@ static int build_graphs(bsb200_chain *ch) {
 
 int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   const double t0 = now_ms();
+  // BSB200_TIMING=1: wall-clock marks of the set-up phases on stderr
+  static const bool timing = std::getenv("BSB200_TIMING") != nullptr;
+  double t_last = t0;
+  auto mark = [&](const char *what) {
+    if (!timing) return;
+    const double t = now_ms();
+    std::fprintf(stderr, "[bsb200 setup r%d] %-22s %8.1f ms\n", a->world > 1 ? a->rank : 0, what, t - t_last);
+    t_last = t;
+  };
   int rc = validate(a);
   if (rc) return rc;
   rc = select_device(a->device);
@@ -315,6 +339,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if (G > 4096) return fail(BSB200_ERR_INVALID, "groups = %d out of range", G);
   rc = make_shard_plan(n, a->nbr_ptr, a->nbr_idx, G, world, rank, ch->plan);
   if (rc) return rc;
+  mark("validate+shard plan");
   const ShardPlan &plan = ch->plan;
   ch->G = G; ch->lo = plan.lo; ch->hi = plan.hi; ch->n_own = plan.n_own();
   const int64_t n_own = ch->n_own, n_local = plan.n_local();
@@ -337,13 +362,17 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
     if (rc) return rc;
   }
+  mark("colouring");
   ch->ord.build(n, colour.data(), ncol, G, choose_segment(n), plan.g0, plan.g1, plan.lo, plan.hi);
   const SpotOrder &ord = ch->ord;
+  mark("spot order");
   if (world > 1) {
     rc = make_halo_plan(plan, a->nbr_ptr, a->nbr_idx, colour.data(), ncol, ord.inv, ch->halo);
     if (rc) return rc;
+    mark("halo plan");
     rc = ch->comm.init(world, rank, a->comm_id);
     if (rc) return rc;
+    mark("comm init");
   }
 
   // ---- device staging --------------------------------------------------------------------------
@@ -378,6 +407,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if ((rc = upload(ch->orig, origp.data(), origp.size(), s))) return rc;
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }
+  mark("ELL/z/orig staging");
   if ((rc = upload(ch->seg_begin, ord.seg_begin.data(), ord.seg_begin.size(), s))) return rc;
   if ((rc = upload(ch->seg_count, ord.seg_count.data(), ord.seg_count.size(), s))) return rc;
   if ((rc = upload(ch->seg_slot, ord.seg_slot.data(), ord.seg_slot.size(), s))) return rc;
@@ -385,7 +415,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if (world > 1) {
     if ((rc = upload(ch->send_pos, ch->halo.send_pos.data(), ch->halo.send_pos.size(), s))) return rc;
     if ((rc = upload(ch->recv_pos, ch->halo.recv_pos.data(), ch->halo.recv_pos.size(), s))) return rc;
-    if ((rc = ch->halo_send.alloc(ch->halo.send_pos.size())) || (rc = ch->halo_recv.alloc(ch->halo.recv_pos.size()))) return rc;
+    if (!ch->comm.peer() &&
+        ((rc = ch->halo_send.alloc(ch->halo.send_pos.size())) || (rc = ch->halo_recv.alloc(ch->halo.recv_pos.size()))))
+      return rc;
   }
   {
     // own rows of Y (R's column-major n x d): one strided copy; column means from per-shard sums
@@ -400,10 +432,15 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     CK(cudaMemsetAsync(ch->Y.p, 0, sizeof(double) * d * ch->ld, s));
     CK(cudaMemsetAsync(gcol.p, 0, sizeof(double) * G * d, s));
     launch_colsums_groups(Yraw.p, n_own, glo.p, plan.lo, d, plan.g0, plan.g1 - plan.g0, gcol.p, s);
-    if (world > 1 && (rc = ch->comm.allgather_f64(gcol.p, (size_t) (plan.g1 - plan.g0) * d, s))) return rc;
+    if (world > 1 && !ch->comm.peer() && (rc = ch->comm.allgather_f64(gcol.p, (size_t) (plan.g1 - plan.g0) * d, s))) return rc;
     std::vector<double> gs((size_t) G * d);
     CK(cudaMemcpyAsync(gs.data(), gcol.p, sizeof(double) * G * d, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (ch->comm.peer()) {   // the shard sums of the other ranks come through the host rendezvous
+      const size_t cnt = (size_t) (plan.g1 - plan.g0) * d;
+      std::vector<double> mine(gs.begin() + (size_t) plan.g0 * d, gs.begin() + (size_t) plan.g0 * d + cnt);
+      if ((rc = ch->comm.host_allgather(mine.data(), cnt * sizeof(double), gs.data()))) return rc;
+    }
     ch->ybar_host.assign((size_t) d, 0.0);
     for (int c = 0; c < d; c++) {
       double acc = 0.0;
@@ -414,6 +451,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     launch_permute_center(Yraw.p, n_own, n_own, d, ch->orig.p, ch->ybar.p, ch->Y.p, ch->ld, s, plan.lo);
     CK(cudaStreamSynchronize(s));
   }
+  mark("Y upload+centre");
   {
     std::vector<double> w1((size_t) ch->ld, 1.0);
     if ((rc = upload(ch->w, w1.data(), w1.size(), s))) return rc;
@@ -438,7 +476,16 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
   const size_t Emax = (size_t) std::max(SL_run.E, SL_init.E);
   if ((rc = ch->partials.alloc((size_t) std::max(ord.nslots, 1) * Emax))) return rc;
-  if ((rc = ch->gsum.alloc((size_t) G * Emax))) return rc;
+  if (ch->comm.peer()) {
+    if ((rc = ch->comm.connect(ch->z.p, (size_t) ch->ld, ch->recv_pos.p, ch->send_pos.p, ch->halo, ncol, (size_t) G * Emax, s)))
+      return rc;
+    ch->gsum_p = ch->comm.gsum();
+    mark("peer windows");
+  } else {
+    if ((rc = ch->gsum.alloc((size_t) G * Emax))) return rc;
+    ch->gsum_p = ch->gsum.p;
+    CK(cudaMemsetAsync(ch->gsum.p, 0, sizeof(double) * G * Emax, s));
+  }
   if ((rc = ch->stats.alloc(Emax))) return rc;
   if ((rc = ch->T_fixed.alloc((size_t) ch->PL.np))) return rc;
   if ((rc = ch->plogLik.alloc((size_t) a->nrep))) return rc;
@@ -450,7 +497,6 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if ((rc = ch->err.alloc(1))) return rc;
   CK(cudaMemsetAsync(ch->iter.p, 0, sizeof(uint32_t), s));
   CK(cudaMemsetAsync(ch->err.p, 0, sizeof(int), s));
-  CK(cudaMemsetAsync(ch->gsum.p, 0, sizeof(double) * G * Emax, s));
   CK(cudaMemsetAsync(ch->snap_mu.p, 0, sizeof(double) * nsnap * q * d, s));
   CK(cudaMemsetAsync(ch->snap_lambda.p, 0, sizeof(double) * nsnap * ch->nl * d * d, s));
   {
@@ -461,6 +507,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   CK(cudaMallocHost(&ch->h_snap_z, sizeof(int32_t) * std::max<int64_t>(n_own, 1)));
   CK(cudaMallocHost(&ch->h_snap_w, sizeof(double) * std::max<int64_t>(n_own, 1)));
 
+  mark("buffers");
   // ---- statistics of the initial state -----------------------------------------------------------
   param_kernel_init();
   if (nlT == 0) {   // normal model, shared precision: sum_j y_j y_j^T never changes -> T_fixed
@@ -477,7 +524,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   if (ch->comm_rc) return ch->comm_rc;
+  mark("initial statistics");
   if ((rc = build_graphs(ch.get()))) return rc;
+  mark("graph capture");
   ch->setup_ms = now_ms() - t0;
   *out = ch.release();
   return BSB200_OK;
@@ -571,11 +620,12 @@ int bsb200_chain_run(bsb200_chain *chain, int32_t iters, double *device_ms) {
   return chain_run_impl(chain, iters, nullptr, device_ms, false);
 }
 
-int bsb200_chain_profile(bsb200_chain *ch, int32_t iters, double *sweep_ms, int64_t *launches, double *param_ms) {
+int bsb200_chain_profile(bsb200_chain *ch, int32_t iters, double *sweep_ms, int64_t *launches, double *param_ms,
+                         double *halo_ms) {
   if (!ch || iters < 0) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
   CK(cudaSetDevice(ch->device));
   cudaStream_t s = ch->stream;
-  const int per_iter = ch->ord.ncol + 1;
+  const int per_iter = 2 * ch->ord.ncol + 1;
   std::vector<cudaEvent_t> ev((size_t) iters * per_iter * 2);
   for (auto &e : ev) CK(cudaEventCreate(&e));
   size_t k = 0;
@@ -587,12 +637,14 @@ int bsb200_chain_profile(bsb200_chain *ch, int32_t iters, double *sweep_ms, int6
       CK(cudaEventRecord(ev[k++], s));
       ch->enqueue_sweep(c, 0, 0, s);
       CK(cudaEventRecord(ev[k++], s));
+      CK(cudaEventRecord(ev[k++], s));
       ch->enqueue_halo(c, s);
+      CK(cudaEventRecord(ev[k++], s));
     }
     ch->iters_done++;
   }
   CK(cudaStreamSynchronize(s));
-  double sw = 0.0, pm = 0.0;
+  double sw = 0.0, pm = 0.0, hm = 0.0;
   int64_t nl = 0;
   k = 0;
   for (int i = 0; i < iters; i++) {
@@ -602,11 +654,14 @@ int bsb200_chain_profile(bsb200_chain *ch, int32_t iters, double *sweep_ms, int6
     for (int c = 0; c < ch->ord.ncol; c++) {
       CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
       sw += ms; k += 2; nl++;
+      CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      hm += ms; k += 2;
     }
   }
   for (auto &e : ev) cudaEventDestroy(e);
   if (sweep_ms) *sweep_ms = sw;
   if (param_ms) *param_ms = pm;
+  if (halo_ms) *halo_ms = hm;
   if (launches) *launches = nl;
   return check_device_error(ch);
 }

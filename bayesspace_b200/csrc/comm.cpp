@@ -1,12 +1,23 @@
-// comm.cpp -- run-time binding of NCCL for the spot-sharded chain (see comm.hpp).
+// comm.cpp -- the transports of the spot-sharded chain (see comm.hpp): peer-memory stores with epoch flags
+// (CUDA IPC, host rendezvous in POSIX shared memory) and the run-time-bound NCCL baseline.
 #include "comm.hpp"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 
 #include "common.hpp"
+#include "shard.hpp"
 
 namespace bsb {
 namespace {
@@ -64,42 +75,409 @@ int nccl_fail(ncclResult_t r, const char *what) {
     if (r_ != ncclSuccess) return nccl_fail(r_, what); \
   } while (0)
 
+
+static const char kPeerMagic[8] = {'B', 'S', 'B', 'P', 'E', 'E', 'R', '1'};
+
 int comm_unique_id(void *out128) {
-  NcclApi *a = api();
-  if (!a) return fail(BSB200_ERR_CUDA, "libnccl.so.2 could not be loaded (needed for world > 1)");
-  ncclUniqueId id;
-  NCK(a->GetUniqueId(&id), "GetUniqueId");
-  std::memcpy(out128, &id, NCCL_UNIQUE_ID_BYTES);
+  const char *want = std::getenv("BSB200_COMM");
+  if (want && std::strcmp(want, "nccl") == 0) {
+    NcclApi *a = api();
+    if (!a) return fail(BSB200_ERR_CUDA, "libnccl.so.2 could not be loaded (BSB200_COMM=nccl)");
+    ncclUniqueId id;
+    NCK(a->GetUniqueId(&id), "GetUniqueId");
+    static_assert(NCCL_UNIQUE_ID_BYTES == 128, "bsb200_comm_unique_id hands out 128 bytes");
+    std::memcpy(out128, &id, NCCL_UNIQUE_ID_BYTES);
+    return BSB200_OK;
+  }
+  // peer transport: magic + 16 random bytes that name the rendezvous segment
+  unsigned char id[128] = {};
+  std::memcpy(id, kPeerMagic, 8);
+  bool ok = false;
+  if (FILE *f = std::fopen("/dev/urandom", "rb")) {
+    ok = std::fread(id + 8, 1, 16, f) == 16;
+    std::fclose(f);
+  }
+  if (!ok) {
+    const uint64_t t = (uint64_t) std::chrono::steady_clock::now().time_since_epoch().count();
+    const uint64_t p = (uint64_t) getpid() * 0x9E3779B97F4A7C15ull ^ (uint64_t) (uintptr_t) &id;
+    std::memcpy(id + 8, &t, 8);
+    std::memcpy(id + 16, &p, 8);
+  }
+  std::memcpy(out128, id, 128);
   return BSB200_OK;
 }
 
-Comm::~Comm() {
-  NcclApi *a = api();
-  if (nccl && a && a->CommDestroy) a->CommDestroy((ncclComm_t) nccl);
+// ---- host rendezvous: one POSIX shared-memory segment per communicator ------------------------------------------
+// W slots of kSlot bytes and two sequence counters per rank.  A fresh segment is all zeros, which is the valid
+// initial state, so every rank may create it.  allgather round r: write the slot, publish seq_in = r, read the
+// others once their seq_in reaches r, publish seq_out = r; a slot is rewritten only when every seq_out reached r.
+class ShmRendezvous {
+ public:
+  static constexpr size_t kSlot = 64 * 1024;
+  struct Header {
+    std::atomic<uint32_t> seq_in[kMaxPeerWorld];
+    std::atomic<uint32_t> seq_out[kMaxPeerWorld];
+  };
+  ~ShmRendezvous() {
+    if (base) munmap(base, bytes);
+    if (rank == 0 && !unlinked) shm_unlink(name);
+  }
+  int open(const unsigned char *id16, int world_, int rank_) {
+    world = world_; rank = rank_;
+    static const char *hex = "0123456789abcdef";
+    std::snprintf(name, sizeof(name), "/bsb200-");
+    size_t k = std::strlen(name);
+    for (int i = 0; i < 16; i++) { name[k++] = hex[id16[i] >> 4]; name[k++] = hex[id16[i] & 15]; }
+    name[k] = 0;
+    bytes = 4096 + (size_t) world * kSlot;
+    const int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return fail(BSB200_ERR_CUDA, "shm_open(%s) failed: %s", name, std::strerror(errno));
+    if (ftruncate(fd, (off_t) bytes) != 0) { close(fd); return fail(BSB200_ERR_CUDA, "ftruncate(%s) failed: %s", name, std::strerror(errno)); }
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(BSB200_ERR_CUDA, "mmap(%s) failed: %s", name, std::strerror(errno));
+    base = (unsigned char *) p;
+    hdr = reinterpret_cast<Header *>(base);
+    static_assert(sizeof(Header) <= 4096, "header page");
+    return BSB200_OK;
+  }
+  static double default_timeout() {
+    const char *e = std::getenv("BSB200_RENDEZVOUS_TIMEOUT");   // seconds a rank waits for the others on the host
+    const double v = e ? std::atof(e) : 0.0;
+    return v > 0.0 ? v : 120.0;
+  }
+  int allgather(const void *mine, size_t nbytes, void *all, double timeout_s = default_timeout()) {
+    if (nbytes > kSlot) return fail(BSB200_ERR_INVALID, "rendezvous message of %zu bytes exceeds the slot", nbytes);
+    const uint32_t r = ++round;
+    int rc;
+    for (int p = 0; p < world; p++)   // everyone is done reading the previous round
+      if ((rc = wait(hdr->seq_out[p], r - 1, p, timeout_s))) return rc;
+    std::memcpy(base + 4096 + (size_t) rank * kSlot, mine, nbytes);
+    hdr->seq_in[rank].store(r, std::memory_order_release);
+    for (int p = 0; p < world; p++) {
+      if ((rc = wait(hdr->seq_in[p], r, p, timeout_s))) return rc;
+      std::memcpy((unsigned char *) all + (size_t) p * nbytes, base + 4096 + (size_t) p * kSlot, nbytes);
+    }
+    hdr->seq_out[rank].store(r, std::memory_order_release);
+    if (rank == 0 && !unlinked) {   // every rank has the segment mapped: the name can go
+      shm_unlink(name);
+      unlinked = true;
+    }
+    return BSB200_OK;
+  }
+
+ private:
+  int wait(std::atomic<uint32_t> &a, uint32_t target, int peer, double timeout_s) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0; (int32_t) (a.load(std::memory_order_acquire) - target) < 0; spin++) {
+      if (spin < 2000) continue;
+      if ((spin & 63) == 0) {
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
+          return fail(BSB200_ERR_CUDA, "rank %d waited %.0f s for rank %d at the rendezvous (different ids, or a rank died?)",
+                      rank, timeout_s, peer);
+        usleep(50);
+      } else {
+        sched_yield();
+      }
+    }
+    return BSB200_OK;
+  }
+  char name[64] = {};
+  unsigned char *base = nullptr;
+  Header *hdr = nullptr;
+  size_t bytes = 0;
+  int world = 1, rank = 0;
+  uint32_t round = 0;
+  bool unlinked = false;
+};
+
+// ---- device side of the peer transport ----------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait for a peer's epoch.  Once any error is latched nobody waits any more (flags are still sent), so a
+// failed rank drains the captured graph instead of stalling its peers for one timeout per wait.
+__device__ void wait_flag(const uint32_t *flag, uint32_t epoch, int *err) {
+  if (*(volatile int *) err) return;
+  const unsigned long long t0 = global_ns();
+  while ((int32_t) (ld_acquire_sys(flag) - epoch) < 0) {
+    __nanosleep(32);
+    if (global_ns() - t0 > BSB_PEER_TIMEOUT_NS) {
+      atomicCAS(err, 0, BSB_DEVERR_PEER_TIMEOUT);
+      return;
+    }
+  }
+}
+
+// One CTA per neighbouring rank: store the boundary labels of the colour just swept into the neighbour's ghost
+// slots, release the neighbour's flag, then wait until the neighbour's own labels of this colour have landed here.
+// WAR safety: the slots written belong to the colour just swept, which the neighbour reads only in LATER phases,
+// and a rank can be at most one phase ahead of a neighbour because each phase ends with this wait.
+__global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const uint8_t *z, const int32_t *send_pos,
+                                                   const int32_t *send_dst, uint32_t *counters, int world, int *err) {
+  const HaloLeg L = legs[blockIdx.x];
+  for (int k = L.s0 + (int) threadIdx.x; k < L.s1; k += 256) L.peer_z[send_dst[k]] = z[send_pos[k]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (L.s1 > L.s0) {
+      const uint32_t e = counters[L.peer] + 1u;
+      counters[L.peer] = e;
+      st_release_sys(L.peer_flag, e);
+    }
+    if (L.nrecv > 0) {
+      const uint32_t e = counters[world + L.peer] + 1u;
+      counters[world + L.peer] = e;
+      wait_flag(L.my_flag, e, err);
+    }
+  }
+}
+
+// One CTA per peer: store this rank's shard sums into the peer's window (parity of the new epoch), release, wait
+// for the peer's sums.  The last CTA to finish publishes the epoch, which k_param reads as its parity.
+__global__ void __launch_bounds__(256) k_gather_peer(const GatherLeg *legs, const double *my_gsum, size_t stride,
+                                                     size_t offset, size_t count, uint32_t *counters, int world,
+                                                     int *err) {
+  const GatherLeg L = legs[blockIdx.x];
+  const uint32_t e = counters[2 * world] + 1u;
+  const size_t base = (size_t) (e & 1u) * stride + offset;
+  const double *src = my_gsum + base;
+  double *dst = L.peer_gsum + base;
+  for (size_t i = threadIdx.x; i < count; i += 256) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys(L.peer_flag, e);
+    wait_flag(L.my_flag, e, err);
+    __threadfence();
+    const uint32_t done = atomicAdd(&counters[2 * world + 1], 1u);
+    if (done == gridDim.x - 1) {
+      counters[2 * world + 1] = 0u;
+      counters[2 * world] = e;
+    }
+  }
+}
+
+}   // namespace
+
+#define CKC(call)                                                                                              \
+  do {                                                                                                         \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                     \
+      return fail(BSB200_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__);      \
+  } while (0)
+
+Comm::~Comm() { shutdown(); }
+
+void Comm::shutdown() {
+  if (transport == NCCL) {
+    NcclApi *a = api();
+    if (nccl && a && a->CommDestroy) a->CommDestroy((ncclComm_t) nccl);
+    nccl = nullptr;
+  }
+  if (transport == PEER) {
+    for (int p = 0; p < world; p++) {
+      if (peer_window[p]) cudaIpcCloseMemHandle(peer_window[p]);
+      if (peer_z[p]) cudaIpcCloseMemHandle(peer_z[p]);
+      if (peer_recv_pos[p]) cudaIpcCloseMemHandle(peer_recv_pos[p]);
+      peer_window[p] = peer_z[p] = peer_recv_pos[p] = nullptr;
+    }
+    if (shm && window) {   // nobody frees exported memory while a peer still has it mapped
+      char one = 1, all[kMaxPeerWorld];
+      shm->allgather(&one, 1, all, 10.0);
+    }
+    if (window) cudaFree(window);
+    if (send_dst) cudaFree(send_dst);
+    if (halo_legs) cudaFree(halo_legs);
+    if (gather_legs) cudaFree(gather_legs);
+    if (counters) cudaFree(counters);
+    window = nullptr; send_dst = nullptr; halo_legs = nullptr; gather_legs = nullptr; counters = nullptr;
+    delete shm;
+    shm = nullptr;
+  }
+  transport = NONE;
 }
 
 int Comm::init(int world_, int rank_, const void *unique_id128) {
-  NcclApi *a = api();
-  if (!a) return fail(BSB200_ERR_CUDA, "libnccl.so.2 could not be loaded (needed for world > 1)");
   if (!unique_id128) return fail(BSB200_ERR_INVALID, "world > 1 needs the communicator id of bsb200_comm_unique_id()");
   world = world_; rank = rank_;
-  ncclUniqueId id;
-  std::memcpy(&id, unique_id128, NCCL_UNIQUE_ID_BYTES);
+  const unsigned char *id = (const unsigned char *) unique_id128;
+  if (std::memcmp(id, kPeerMagic, 8) == 0) {
+    if (world > kMaxPeerWorld) return fail(BSB200_ERR_UNSUPPORTED, "the peer transport serves up to %d ranks of one box", kMaxPeerWorld);
+    shm = new (std::nothrow) ShmRendezvous();
+    if (!shm) return fail(BSB200_ERR_BUFFER, "out of memory");
+    int rc = shm->open(id + 8, world, rank);
+    if (rc) return rc;
+    transport = PEER;
+    // every pair must be able to reach each other's memory
+    int dev = 0;
+    CKC(cudaGetDevice(&dev));
+    std::vector<int> devs((size_t) world);
+    if ((rc = shm->allgather(&dev, sizeof(int), devs.data()))) return rc;
+    for (int p = 0; p < world; p++) {
+      if (p == rank) continue;
+      if (devs[(size_t) p] == dev)
+        return fail(BSB200_ERR_INVALID, "ranks %d and %d use the same GPU %d (one process per GPU)", rank, p, dev);
+      int can = 0;
+      CKC(cudaDeviceCanAccessPeer(&can, dev, devs[(size_t) p]));
+      if (!can)
+        return fail(BSB200_ERR_UNSUPPORTED, "GPU %d cannot access GPU %d's memory: make the id with BSB200_COMM=nccl", dev,
+                    devs[(size_t) p]);
+    }
+    return BSB200_OK;
+  }
+  NcclApi *a = api();
+  if (!a) return fail(BSB200_ERR_CUDA, "libnccl.so.2 could not be loaded (needed for an NCCL communicator id)");
+  ncclUniqueId nid;
+  std::memcpy(&nid, unique_id128, NCCL_UNIQUE_ID_BYTES);
   ncclComm_t c = nullptr;
-  NCK(a->CommInitRank(&c, world, id, rank), "CommInitRank");
+  NCK(a->CommInitRank(&c, world, nid, rank), "CommInitRank");
   nccl = c;
+  transport = NCCL;
   return BSB200_OK;
+}
+
+int Comm::host_allgather(const void *mine, size_t bytes, void *all) {
+  if (transport != PEER) return fail(BSB200_ERR_INVALID, "host_allgather needs the peer transport");
+  return shm->allgather(mine, bytes, all);
+}
+
+namespace {
+struct ConnectHead {
+  cudaIpcMemHandle_t h_window, h_z, h_recv;
+  uint32_t window_magic;
+  int32_t has_recv, n_off, recv_total;
+};
+}   // namespace
+
+int Comm::connect(uint8_t *z, size_t z_bytes, const int32_t *recv_pos_dev, const int32_t *send_pos_dev, const HaloPlan &halo,
+                  int ncol_, size_t gsum_doubles, cudaStream_t s) {
+  (void) z_bytes; (void) send_pos_dev;
+  if (transport != PEER) return BSB200_OK;
+  ncol = ncol_;
+  const int W = world;
+  const size_t n_off = (size_t) ncol * W + 1;
+  if (sizeof(ConnectHead) + n_off * sizeof(int32_t) > ShmRendezvous::kSlot)
+    return fail(BSB200_ERR_UNSUPPORTED, "%d colours x %d ranks exceed the rendezvous slot", ncol, W);
+  gsum_stride = (gsum_doubles + 1) & ~(size_t) 1;
+  window_bytes = 4096 + 2 * gsum_stride * sizeof(double);
+  CKC(cudaMalloc((void **) &window, window_bytes));
+  CKC(cudaMemsetAsync(window, 0, window_bytes, s));
+  const uint32_t magic = 0xB5B20000u + (uint32_t) rank;
+  CKC(cudaMemcpyAsync(window + 4092, &magic, 4, cudaMemcpyHostToDevice, s));
+  CKC(cudaMalloc((void **) &counters, sizeof(uint32_t) * (2 * (size_t) W + 2)));
+  CKC(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (2 * (size_t) W + 2), s));
+  CKC(cudaStreamSynchronize(s));
+
+  std::vector<unsigned char> msg(sizeof(ConnectHead) + n_off * sizeof(int32_t)), all(msg.size() * (size_t) W);
+  ConnectHead head{};
+  CKC(cudaIpcGetMemHandle(&head.h_window, window));
+  CKC(cudaIpcGetMemHandle(&head.h_z, z));
+  head.has_recv = recv_pos_dev != nullptr && halo.recv_total() > 0;
+  if (head.has_recv) CKC(cudaIpcGetMemHandle(&head.h_recv, (void *) recv_pos_dev));
+  head.window_magic = magic;
+  head.n_off = (int32_t) n_off;
+  head.recv_total = (int32_t) halo.recv_total();
+  std::memcpy(msg.data(), &head, sizeof(head));
+  std::memcpy(msg.data() + sizeof(head), halo.recv_off.data(), n_off * sizeof(int32_t));
+  int rc = shm->allgather(msg.data(), msg.size(), all.data());
+  if (rc) return rc;
+
+  // map the peers this rank talks to: everyone's window (shard sums), the halo neighbours' labels and receive lists
+  std::vector<HaloLeg> legs((size_t) ncol * (size_t) (W - 1));
+  halo_leg_count.assign((size_t) ncol, 0);
+  const size_t send_total = (size_t) halo.send_total();
+  if (send_total) CKC(cudaMalloc((void **) &send_dst, sizeof(int32_t) * send_total));
+  for (int p = 0; p < W; p++) {
+    if (p == rank) continue;
+    ConnectHead ph;
+    std::memcpy(&ph, all.data() + (size_t) p * msg.size(), sizeof(ph));
+    const int32_t *poff = reinterpret_cast<const int32_t *>(all.data() + (size_t) p * msg.size() + sizeof(ph));
+    if (ph.n_off != (int32_t) n_off) return fail(BSB200_ERR_INVALID, "rank %d built %d halo offsets, rank %d %d", p, ph.n_off, rank, (int) n_off);
+    CKC(cudaIpcOpenMemHandle(&peer_window[p], ph.h_window, cudaIpcMemLazyEnablePeerAccess));
+    uint32_t seen = 0;
+    CKC(cudaMemcpy(&seen, (uint8_t *) peer_window[p] + 4092, 4, cudaMemcpyDeviceToHost));
+    if (seen != ph.window_magic) return fail(BSB200_ERR_CUDA, "mapped window of rank %d does not carry its tag", p);
+    bool neighbour = false;
+    for (int c = 0; c < ncol; c++) {
+      const size_t e = (size_t) c * W + p;
+      neighbour |= halo.send_off[e + 1] > halo.send_off[e] || halo.recv_off[e + 1] > halo.recv_off[e];
+    }
+    if (!neighbour) continue;
+    CKC(cudaIpcOpenMemHandle(&peer_z[p], ph.h_z, cudaIpcMemLazyEnablePeerAccess));
+    if (ph.has_recv) CKC(cudaIpcOpenMemHandle(&peer_recv_pos[p], ph.h_recv, cudaIpcMemLazyEnablePeerAccess));
+    for (int c = 0; c < ncol; c++) {
+      const size_t e = (size_t) c * W + p;
+      const int32_t s0 = halo.send_off[e], s1 = halo.send_off[e + 1];
+      const int32_t nrecv = halo.recv_off[e + 1] - halo.recv_off[e];
+      // the peer's receive list from this rank, same colour: positions in ITS label array, same order as our sends
+      const size_t pe = (size_t) c * W + rank;
+      const int32_t r0 = poff[pe], r1 = poff[pe + 1];
+      if (r1 - r0 != s1 - s0)
+        return fail(BSB200_ERR_INVALID, "halo lists of ranks %d and %d disagree for colour %d (%d vs %d)", rank, p, c, s1 - s0, r1 - r0);
+      if (s1 == s0 && nrecv == 0) continue;
+      if (s1 > s0) {
+        if (!peer_recv_pos[p]) return fail(BSB200_ERR_INVALID, "rank %d exported no receive list", p);
+        CKC(cudaMemcpyAsync(send_dst + s0, (const int32_t *) peer_recv_pos[p] + r0, sizeof(int32_t) * (size_t) (s1 - s0),
+                            cudaMemcpyDefault, s));
+      }
+      HaloLeg L{};
+      L.peer_z = (uint8_t *) peer_z[p];
+      L.peer_flag = reinterpret_cast<uint32_t *>(peer_window[p]) + rank;
+      L.my_flag = reinterpret_cast<const uint32_t *>(window) + p;
+      L.s0 = s0; L.s1 = s1; L.nrecv = nrecv; L.peer = p;
+      legs[(size_t) c * (size_t) (W - 1) + (size_t) halo_leg_count[(size_t) c]++] = L;
+    }
+  }
+  std::vector<GatherLeg> glegs((size_t) (W - 1));
+  for (int i = 0; i < W - 1; i++) {
+    const int p = (rank + 1 + i) % W;
+    GatherLeg g{};
+    g.peer_gsum = reinterpret_cast<double *>((uint8_t *) peer_window[p] + 4096);
+    g.peer_flag = reinterpret_cast<uint32_t *>(peer_window[p]) + 64 + rank;
+    g.my_flag = reinterpret_cast<const uint32_t *>(window) + 64 + p;
+    g.peer = p;
+    glegs[(size_t) i] = g;
+  }
+  CKC(cudaMalloc((void **) &halo_legs, sizeof(HaloLeg) * std::max<size_t>(legs.size(), 1)));
+  CKC(cudaMalloc((void **) &gather_legs, sizeof(GatherLeg) * glegs.size()));
+  CKC(cudaMemcpyAsync(halo_legs, legs.data(), sizeof(HaloLeg) * legs.size(), cudaMemcpyHostToDevice, s));
+  CKC(cudaMemcpyAsync(gather_legs, glegs.data(), sizeof(GatherLeg) * glegs.size(), cudaMemcpyHostToDevice, s));
+  CKC(cudaStreamSynchronize(s));
+  // nobody starts the data path before every rank has read the receive lists it needs
+  char one = 1, seen_all[kMaxPeerWorld];
+  return shm->allgather(&one, 1, seen_all);
+}
+
+void Comm::enqueue_halo_peer(int colour, const uint8_t *z, const int32_t *send_pos_dev, int *err, cudaStream_t s) {
+  const int nlegs = halo_leg_count[(size_t) colour];
+  if (nlegs == 0) return;
+  k_halo_peer<<<nlegs, 256, 0, s>>>(halo_legs + (size_t) colour * (size_t) (world - 1), z, send_pos_dev, send_dst, counters,
+                                    world, err);
+  g_launches++;
+}
+
+void Comm::enqueue_gather_peer(size_t offset_doubles, size_t count_doubles, int *err, cudaStream_t s) {
+  k_gather_peer<<<world - 1, 256, 0, s>>>(gather_legs, gsum(), gsum_stride, offset_doubles, count_doubles, counters, world,
+                                          err);
+  g_launches++;
 }
 
 int Comm::allgather_f64(double *buf, size_t count, cudaStream_t s) {
   NcclApi *a = api();
   NCK(a->AllGather(buf + (size_t) rank * count, buf, count, ncclFloat64, (ncclComm_t) nccl, s), "AllGather");
-  return BSB200_OK;
-}
-
-int Comm::allreduce_max_f64(double *buf, size_t count, cudaStream_t s) {
-  NcclApi *a = api();
-  NCK(a->AllReduce(buf, buf, count, ncclFloat64, ncclMax, (ncclComm_t) nccl, s), "AllReduce");
   return BSB200_OK;
 }
 

@@ -125,6 +125,8 @@ struct ParamArgs {
   int ngroups;
   double *gsum;                 // ngroups * E scratch
   int gsum_ready;               // level 1 already done by k_reduce_groups
+  const uint32_t *gepoch;       // peer transport: shard sums are double buffered, parity = *gepoch & 1 (else null)
+  size_t gsum_stride;           // doubles between the two parities
   double *stats;                // E reduced statistics (kept for probes)
   const double *T_fixed;        // np: sum y y^T (normal model, shared precision) or nullptr
   const double *mu0c;           // d   mu0 - ybar

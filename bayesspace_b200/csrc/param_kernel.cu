@@ -184,16 +184,17 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
   BSB_T(0);
 
   // ---- (0) deterministic two-level reduction of the segment partials ---------------------------
+  double *const gsum = a.gsum + (a.gepoch ? (size_t) (*a.gepoch & 1u) * a.gsum_stride : (size_t) 0);
   for (int idx = tid; !a.gsum_ready && idx < E * a.ngroups; idx += nt) {
     const int e = idx % E, g = idx / E;
     double s = 0.0;
     for (int slot = a.group_start[g]; slot < a.group_start[g + 1]; slot++) s += a.partials[(size_t) slot * E + e];
-    a.gsum[(size_t) g * E + e] = s;
+    gsum[(size_t) g * E + e] = s;
   }
   __syncthreads();
   for (int e = tid; e < E; e += nt) {
     // shard sums folded in shard order (fixed association); loads issued 8 at a time ahead of the adds
-    const double *gp = a.gsum + e;
+    const double *gp = gsum + e;
     double s = 0.0;
     int g = 0;
     for (; g + 8 <= a.ngroups; g += 8) {

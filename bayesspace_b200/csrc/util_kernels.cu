@@ -60,12 +60,13 @@ __global__ void k_running_mean(const double *snap, double *mean, int64_t len, do
 // Level 1 of the two-level statistics reduction when there are many segments: one thread per
 // (group, entry), sequential over the group's slots (fixed order).
 __global__ void __launch_bounds__(256) k_reduce_groups(const double *partials, const int32_t *group_start, int E,
-                                                      double *gsum) {
+                                                      double *gsum, const uint32_t *gepoch, size_t par_stride) {
   // CTA = 32 entries x 8 sub-ranges of the group's slots.  Each thread folds its sub-range with four interleaved
   // running sums, the 8 sub-range sums are then folded in order: a fixed association that depends only on the
   // group's slot count (a global quantity), never on the grid or the GPU count.
   __shared__ double sub[8][33];
   const int le = threadIdx.x & 31, sr = threadIdx.x >> 5, e = blockIdx.x * 32 + le, g = blockIdx.y;
+  if (gepoch) gsum += (size_t) ((*gepoch + 1u) & 1u) * par_stride;   // the parity the coming gather publishes
   const int begin = group_start[g], end = group_start[g + 1];
   const int len = (end - begin + 7) / 8;
   int slot = begin + sr * len;
@@ -203,9 +204,9 @@ void launch_running_mean(const double *snap, double *mean, int64_t len, double i
   g_launches++;
 }
 void launch_reduce_groups(const double *partials, const int32_t *group_start, int ngroups, int E,
-                          double *gsum, cudaStream_t s) {
+                          double *gsum, cudaStream_t s, const uint32_t *gepoch, size_t par_stride) {
   dim3 grid((E + 31) / 32, ngroups);
-  k_reduce_groups<<<grid, 256, 0, s>>>(partials, group_start, E, gsum);
+  k_reduce_groups<<<grid, 256, 0, s>>>(partials, group_start, E, gsum, gepoch, par_stride);
   g_launches++;
 }
 void launch_factor(const double *mat, int nl, int d, int form, double *rooti, double *logdet, int *err,

@@ -21,7 +21,7 @@ void launch_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, c
                        const double *ybar, double *out, int64_t dst_ld, cudaStream_t s);
 void launch_running_mean(const double *snap, double *mean, int64_t len, double inv_count, cudaStream_t s);
 void launch_reduce_groups(const double *partials, const int32_t *group_start, int ngroups, int E,
-                          double *gsum, cudaStream_t s);
+                          double *gsum, cudaStream_t s, const uint32_t *gepoch = nullptr, size_t par_stride = 0);
 void launch_factor(const double *mat, int nl, int d, int form, double *rooti, double *logdet, int *err,
                    cudaStream_t s);
 void launch_scatter_probe(const double *stats, const StatLayout &SL, const double *mu, int nl, double *S,

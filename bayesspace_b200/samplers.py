@@ -224,9 +224,9 @@ class Chain:
         return ms.value
 
     def profile(self, iters):
-        sw, pm, nl = C.c_double(0), C.c_double(0), C.c_int64(0)
-        check(lib().bsb200_chain_profile(self._h, int(iters), C.byref(sw), C.byref(nl), C.byref(pm)))
-        return {"sweep_ms": sw.value, "sweep_launches": int(nl.value), "param_ms": pm.value}
+        sw, pm, hm, nl = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int64(0)
+        check(lib().bsb200_chain_profile(self._h, int(iters), C.byref(sw), C.byref(nl), C.byref(pm), C.byref(hm)))
+        return {"sweep_ms": sw.value, "sweep_launches": int(nl.value), "param_ms": pm.value, "halo_ms": hm.value}
 
     def state(self):
         z = np.zeros(self.n, dtype=np.int32)

@@ -46,50 +46,93 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """SM clock and throttle reasons of the job's GPUs while the timed region runs.
+
+    NVML is polled in-process (pynvml, the library nvidia-smi itself reads) from a thread that is started BEFORE
+    the warm-up, so that no NVML initialisation or nvidia-smi process start-up lands inside the timed region
+    (with 8 ranks each spawning nvidia-smi the driver-wide locks it takes doubled the measured step time).
+    Only samples taken between mark() and stop() are reported.  Falls back to one nvidia-smi -lms process."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+    def __init__(self, gpus, period_s=0.05):
+        self.gpus, self.rows, self.proc, self.period = list(gpus), [], None, period_s
+        self.stop_flag, self.first, self.t, self.mode, self.t0 = threading.Event(), threading.Event(), None, None, 0
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(g) for g in self.gpus]
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(map(str, self.gpus)),
+                                              "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.mode = "nvidia-smi"
+                self.t = threading.Thread(target=self._read_smi, daemon=True)
+                self.t.start()
+            except Exception:
+                self.mode = None
+        if self.mode:
+            self.first.wait(timeout=10.0)
+        return self
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        mx = [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in self.handles]
+        while not self.stop_flag.is_set():
+            for h, m in zip(self.handles, mx):
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    self.rows.append((time.perf_counter(), float(sm), float(m), [n for b, n in bits if r & b]))
+                except Exception:
+                    pass
+            self.first.set()
+            self.stop_flag.wait(self.period)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
-            if len(f) >= 7:
-                self.rows.append(f)
+            if len(f) >= 6:
+                try:
+                    self.rows.append((time.perf_counter(), float(f[0]), float(f[1]),
+                                      [n for n, v in zip(self.NAMES, f[2:6]) if v == "Active"]))
+                except ValueError:
+                    pass
+                self.first.set()
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for f in self.rows:
+        if not self.mode:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(self.NAMES, f[3:7]):
-                if v == "Active":
-                    reasons.add(name)
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        self.t.join(timeout=2)
+        rows = [r for r in self.rows if r[0] >= self.t0] or self.rows[-len(self.gpus):]
+        sm, mx, reasons = [r[1] for r in rows], [r[2] for r in rows], set()
+        for r in rows:
+            reasons.update(r[3])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.mode, "gpus": self.gpus}
 
 
 def ncu_traffic(name):
@@ -283,13 +326,15 @@ def run_gpu(args):
     shard_kw = dict(world=world, rank=rank, comm_id=comm_id()) if sharded else {}
     ch = B.Chain(*chain_args(w, csr, nrep, thin), model=w.model, precision=w.precision,
                  seed=149 + (0 if sharded else rank), device=local, colour=colour, **shard_kw)
+    # rank 0 watches every GPU of the job; the sampler is up (first sample in) before the warm-up starts
+    clocks = ClockSampler(range(world) if rank == 0 else []).start() if rank == 0 else None
     ch.run(W)
-    clocks = ClockSampler(local)
     if dist:
         import torch
         dist.barrier()
         torch.cuda.synchronize()
-    clocks.start()
+    if clocks:
+        clocks.mark()
     l0 = B.kernel_launches()
     ms = ch.run(K)   # CUDA events on the library's stream around the K captured iterations
     launches = B.kernel_launches() - l0
@@ -301,7 +346,7 @@ def run_gpu(args):
         ms = float(t.item())
         dist.barrier()
     prof = ch.profile(min(K, 50))
-    ck = clocks.stop()
+    ck = clocks.stop() if clocks else None
     ch.close()
     # ---- end to end through the C ABI with host buffers (bsb200_cluster: H2D, chain, snapshots D2H) ------
     e2e_iters = args.e2e_iters
@@ -341,7 +386,8 @@ def run_gpu(args):
                          "traffic_source": "profiles/r1_sweep_%s_ncu.json (ncu --set full, bytes per launch)" % args.workload,
                          "algorithmic_bytes_per_spot_update": Bspot, "bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sweep_ms_per_launch, "formula": ALGO_NOTE,
-                         "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50))},
+                         "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50)),
+                         "halo_exchange_ms_per_iter": prof["halo_ms"] / max(1, min(K, 50))},
             "gpu_launches": int(launches), "clocks": ck}
     nsnap = (e2e_iters + 1) // 100
     h2d = w.n * w.d * 8 + w.n * 4 + len(csr[1]) * 4 + (w.n + 1) * 8

@@ -166,9 +166,10 @@ int bsb200_chain_create(const bsb200_cluster_args *args, bsb200_chain **chain);
 /* Advances `iters` iterations (continuing the iteration counter); device time in *device_ms. */
 int bsb200_chain_run(bsb200_chain *chain, int32_t iters, double *device_ms);
 /* As bsb200_chain_run but launches kernel by kernel with CUDA events around every z-sweep launch:
- * sweep_ms = total time inside the sweep kernels, launches = number of sweep launches timed. */
+ * sweep_ms = total time inside the sweep kernels, launches = number of sweep launches timed, param_ms = statistics
+ * fold (+ allgather) + k_param, halo_ms = boundary-label exchanges (0 on a single GPU). */
 int bsb200_chain_profile(bsb200_chain *chain, int32_t iters, double *sweep_ms, int64_t *launches,
-                         double *param_ms);
+                         double *param_ms, double *halo_ms);
 /* Current state in the caller's (original) spot order; NULL pointers are skipped.
  * plogLik receives the values of all iterations run so far (length = iterations done + 1). */
 int bsb200_chain_state(bsb200_chain *chain, int32_t *z, double *weights, double *mu, double *lambda,

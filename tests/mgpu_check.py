@@ -2,7 +2,7 @@
 
 Every rank runs the same chain twice on its own GPU -- alone (world = 1) and as rank r of a spot-sharded chain
 over W GPUs (labels of boundary spots exchanged after every colour phase, per-shard statistics allgathered) --
-with the same number of virtual shards.  The two must agree BIT FOR BIT: labels, weights (own spots), mu,
+with the same number of virtual shards, once per transport (peer-memory stores, NCCL).  The two must agree BIT FOR BIT: labels, weights (own spots), mu,
 lambda and plogLik (north_star: "1/2/4/8-GPU chains are bit-exact").
 """
 import os
@@ -24,7 +24,11 @@ def main():
     rank, W = dist.get_rank(), dist.get_world_size()
     cases = [("small_sq", (64, 64), "iterate", 16), ("small_hex", (60, 40), "iterate_t", 64),
              ("small_sq", (48, 64), "iterate_t_vvv", 8), ("small_hex", (40, 30), "iterate_vvv", 8)]
-    for name, shape, fname, groups in cases:
+    transports = os.environ.get("BSB200_CHECK_TRANSPORTS", "peer,nccl").split(",")
+    for name, shape, fname, groups in [c for c in cases for _ in transports]:
+        transport = transports[0]
+        transports = transports[1:] + transports[:1]
+        os.environ["BSB200_COMM"] = transport   # read when the id is made: peer-memory stores (default) or NCCL
         w = synth.make_workload(name, n_override=shape)
         _, csr = B.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
         colour = B.colour_lattice(w.array_row, w.array_col, w.platform)
@@ -44,7 +48,7 @@ def main():
         assert np.array_equal(shard["plogLik"][1:], alone["plogLik"][1:]), (fname, "plogLik")
         dist.barrier()
         if rank == 0:
-            print("bit-exact", fname, name, shape, "world", W, "plogLik[-1] = %.6f" % alone["plogLik"][-1], flush=True)
+            print("bit-exact", transport, fname, name, shape, "world", W, "plogLik[-1] = %.6f" % alone["plogLik"][-1], flush=True)
     dist.destroy_process_group()
 
 
