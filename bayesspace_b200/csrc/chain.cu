@@ -164,9 +164,9 @@ struct bsb200_chain {
 
   ~bsb200_chain() {
     if (stream) cudaStreamSynchronize(stream);
-    comm.shutdown();               // unmap the peers before the exported label array goes away
-    if (graph_iter) cudaGraphExecDestroy(graph_iter);
+    if (graph_iter) cudaGraphExecDestroy(graph_iter);     // graphs first: NCCL waits for the graphs that captured it
     if (graph_batch) cudaGraphExecDestroy(graph_batch);
+    comm.shutdown();               // unmap the peers before the exported label array goes away
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (h_snap_z) cudaFreeHost(h_snap_z);
@@ -380,6 +380,15 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   cudaStream_t s = ch->stream;
   CK(cudaEventCreate(&ch->ev0));
   CK(cudaEventCreate(&ch->ev1));
+  const int nlT = (ch->tdist || ch->vvv) ? ch->nl : 0;
+  const StatLayout SL_run = make_stat_layout(q, d, nlT);
+  const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
+  const size_t Emax = (size_t) std::max(SL_run.E, SL_init.E);
+  if (ch->comm.peer()) {   // labels, receive list and shard sums live in the arena the peers map
+    if ((rc = ch->comm.alloc_arena((size_t) ch->ld, ch->halo.recv_pos.size(), (size_t) G * Emax, s))) return rc;
+    ch->z.adopt(ch->comm.z(), (size_t) ch->ld);
+    ch->recv_pos.adopt(ch->comm.recv_pos(), ch->halo.recv_pos.size());
+  }
   int maxdeg = 0;
   for (int64_t j = 0; j < n; j++) maxdeg = std::max<int>(maxdeg, (int) (a->nbr_ptr[j + 1] - a->nbr_ptr[j]));
   ch->maxdeg = maxdeg;
@@ -400,7 +409,8 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     }
     for (size_t gi = 0; gi < plan.ghosts.size(); gi++) z0[(size_t) n_own + gi] = (uint8_t) (a->init[plan.ghosts[gi]] - 1);
     if ((rc = upload(ch->ell, ell.data(), ell.size(), s))) return rc;
-    if ((rc = upload(ch->z, z0.data(), z0.size(), s))) return rc;
+    if (ch->comm.peer()) CK(cudaMemcpyAsync(ch->z.p, z0.data(), z0.size(), cudaMemcpyHostToDevice, s));
+    else if ((rc = upload(ch->z, z0.data(), z0.size(), s))) return rc;
     std::vector<int32_t> origp((size_t) ch->ld, 0);
     std::copy(ord.perm.begin(), ord.perm.end(), origp.begin());
     std::copy(plan.ghosts.begin(), plan.ghosts.end(), origp.begin() + n_own);
@@ -414,7 +424,14 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if ((rc = upload(ch->group_start, ord.group_start.data(), ord.group_start.size(), s))) return rc;
   if (world > 1) {
     if ((rc = upload(ch->send_pos, ch->halo.send_pos.data(), ch->halo.send_pos.size(), s))) return rc;
-    if ((rc = upload(ch->recv_pos, ch->halo.recv_pos.data(), ch->halo.recv_pos.size(), s))) return rc;
+    if (ch->comm.peer()) {
+      if (!ch->halo.recv_pos.empty())
+        CK(cudaMemcpyAsync(ch->recv_pos.p, ch->halo.recv_pos.data(), sizeof(int32_t) * ch->halo.recv_pos.size(),
+                           cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    } else if ((rc = upload(ch->recv_pos, ch->halo.recv_pos.data(), ch->halo.recv_pos.size(), s))) {
+      return rc;
+    }
     if (!ch->comm.peer() &&
         ((rc = ch->halo_send.alloc(ch->halo.send_pos.size())) || (rc = ch->halo_recv.alloc(ch->halo.recv_pos.size()))))
       return rc;
@@ -471,14 +488,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     CK(cudaStreamSynchronize(s));
   }
   const int nsnap = a->nrep / a->thin + 1;
-  const int nlT = (ch->tdist || ch->vvv) ? ch->nl : 0;
-  const StatLayout SL_run = make_stat_layout(q, d, nlT);
-  const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
-  const size_t Emax = (size_t) std::max(SL_run.E, SL_init.E);
   if ((rc = ch->partials.alloc((size_t) std::max(ord.nslots, 1) * Emax))) return rc;
   if (ch->comm.peer()) {
-    if ((rc = ch->comm.connect(ch->z.p, (size_t) ch->ld, ch->recv_pos.p, ch->send_pos.p, ch->halo, ncol, (size_t) G * Emax, s)))
-      return rc;
+    if ((rc = ch->comm.connect(ch->halo, ncol, s))) return rc;
     ch->gsum_p = ch->comm.gsum();
     mark("peer windows");
   } else {

@@ -14,12 +14,19 @@ template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t count = 0;
+  bool owned = true;
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p && owned) cudaFree(p); }
+  // a region of somebody else's allocation (the exported arena of the peer transport)
+  void adopt(T *ptr, size_t n) {
+    if (p && owned) cudaFree(p);
+    p = ptr; count = n; owned = false;
+  }
   int alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
+    if (p && owned) cudaFree(p);
+    p = nullptr; owned = true;
     count = n;
     if (n == 0) n = 1;
     cudaError_t e = cudaMalloc(&p, n * sizeof(T));

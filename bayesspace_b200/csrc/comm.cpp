@@ -209,12 +209,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 // Bounded wait for a peer's epoch.  Once any error is latched nobody waits any more (flags are still sent), so a
 // failed rank drains the captured graph instead of stalling its peers for one timeout per wait.
-__device__ void wait_flag(const uint32_t *flag, uint32_t epoch, int *err) {
+__device__ void wait_flag(const uint32_t *flag, uint32_t epoch, int *err, unsigned long long timeout_ns) {
   if (*(volatile int *) err) return;
   const unsigned long long t0 = global_ns();
   while ((int32_t) (ld_acquire_sys(flag) - epoch) < 0) {
     __nanosleep(32);
-    if (global_ns() - t0 > BSB_PEER_TIMEOUT_NS) {
+    if (global_ns() - t0 > timeout_ns) {
       atomicCAS(err, 0, BSB_DEVERR_PEER_TIMEOUT);
       return;
     }
@@ -226,7 +226,8 @@ __device__ void wait_flag(const uint32_t *flag, uint32_t epoch, int *err) {
 // WAR safety: the slots written belong to the colour just swept, which the neighbour reads only in LATER phases,
 // and a rank can be at most one phase ahead of a neighbour because each phase ends with this wait.
 __global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const uint8_t *z, const int32_t *send_pos,
-                                                   const int32_t *send_dst, uint32_t *counters, int world, int *err) {
+                                                   const int32_t *send_dst, uint32_t *counters, int world, int *err,
+                                                   unsigned long long timeout_ns) {
   const HaloLeg L = legs[blockIdx.x];
   for (int k = L.s0 + (int) threadIdx.x; k < L.s1; k += 256) L.peer_z[send_dst[k]] = z[send_pos[k]];
   __threadfence_system();
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const ui
     if (L.nrecv > 0) {
       const uint32_t e = counters[world + L.peer] + 1u;
       counters[world + L.peer] = e;
-      wait_flag(L.my_flag, e, err);
+      wait_flag(L.my_flag, e, err, timeout_ns);
     }
   }
 }
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const ui
 // for the peer's sums.  The last CTA to finish publishes the epoch, which k_param reads as its parity.
 __global__ void __launch_bounds__(256) k_gather_peer(const GatherLeg *legs, const double *my_gsum, size_t stride,
                                                      size_t offset, size_t count, uint32_t *counters, int world,
-                                                     int *err) {
+                                                     int *err, unsigned long long timeout_ns) {
   const GatherLeg L = legs[blockIdx.x];
   const uint32_t e = counters[2 * world] + 1u;
   const size_t base = (size_t) (e & 1u) * stride + offset;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(256) k_gather_peer(const GatherLeg *legs, cons
   __syncthreads();
   if (threadIdx.x == 0) {
     st_release_sys(L.peer_flag, e);
-    wait_flag(L.my_flag, e, err);
+    wait_flag(L.my_flag, e, err, timeout_ns);
     __threadfence();
     const uint32_t done = atomicAdd(&counters[2 * world + 1], 1u);
     if (done == gridDim.x - 1) {
@@ -288,22 +289,21 @@ void Comm::shutdown() {
     nccl = nullptr;
   }
   if (transport == PEER) {
+    bool mapped = false;
     for (int p = 0; p < world; p++) {
-      if (peer_window[p]) cudaIpcCloseMemHandle(peer_window[p]);
-      if (peer_z[p]) cudaIpcCloseMemHandle(peer_z[p]);
-      if (peer_recv_pos[p]) cudaIpcCloseMemHandle(peer_recv_pos[p]);
-      peer_window[p] = peer_z[p] = peer_recv_pos[p] = nullptr;
+      if (peer_base[p]) { cudaIpcCloseMemHandle(peer_base[p]); mapped = true; }
+      peer_base[p] = nullptr; peer_arena[p] = nullptr;
     }
-    if (shm && window) {   // nobody frees exported memory while a peer still has it mapped
+    if (shm && mapped) {   // nobody frees exported memory while a peer still has it mapped
       char one = 1, all[kMaxPeerWorld];
       shm->allgather(&one, 1, all, 10.0);
     }
-    if (window) cudaFree(window);
+    if (arena) cudaFree(arena);
     if (send_dst) cudaFree(send_dst);
     if (halo_legs) cudaFree(halo_legs);
     if (gather_legs) cudaFree(gather_legs);
     if (counters) cudaFree(counters);
-    window = nullptr; send_dst = nullptr; halo_legs = nullptr; gather_legs = nullptr; counters = nullptr;
+    arena = nullptr; send_dst = nullptr; halo_legs = nullptr; gather_legs = nullptr; counters = nullptr;
     delete shm;
     shm = nullptr;
   }
@@ -316,6 +316,10 @@ int Comm::init(int world_, int rank_, const void *unique_id128) {
   const unsigned char *id = (const unsigned char *) unique_id128;
   if (std::memcmp(id, kPeerMagic, 8) == 0) {
     if (world > kMaxPeerWorld) return fail(BSB200_ERR_UNSUPPORTED, "the peer transport serves up to %d ranks of one box", kMaxPeerWorld);
+    if (const char *e = std::getenv("BSB200_PEER_TIMEOUT")) {   // seconds a kernel waits for a peer's flag
+      const double v = std::atof(e);
+      if (v > 0.0) peer_timeout_ns = (uint64_t) (v * 1e9);
+    }
     shm = new (std::nothrow) ShmRendezvous();
     if (!shm) return fail(BSB200_ERR_BUFFER, "out of memory");
     int rc = shm->open(id + 8, world, rank);
@@ -356,68 +360,86 @@ int Comm::host_allgather(const void *mine, size_t bytes, void *all) {
 
 namespace {
 struct ConnectHead {
-  cudaIpcMemHandle_t h_window, h_z, h_recv;
-  uint32_t window_magic;
-  int32_t has_recv, n_off, recv_total;
+  cudaIpcMemHandle_t handle;
+  uint64_t base_off;            // arena - base of the underlying allocation the handle names
+  uint64_t off_recv, off_z, arena_bytes;
+  uint32_t magic;
+  int32_t n_off, recv_total, rank;
 };
+
+// offset of a device pointer inside the allocation cudaIpcGetMemHandle exports (driver API through the runtime)
+int allocation_offset(const void *ptr, uint64_t *off) {
+  typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  CKC(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  if (!fn || qr != cudaDriverEntryPointSuccess) return fail(BSB200_ERR_CUDA, "cuMemGetAddressRange is not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int r = reinterpret_cast<range_fn>(fn)(&base, &size, (unsigned long long) (uintptr_t) ptr);
+  if (r != 0) return fail(BSB200_ERR_CUDA, "cuMemGetAddressRange failed (%d)", r);
+  *off = (uint64_t) ((unsigned long long) (uintptr_t) ptr - base);
+  return BSB200_OK;
+}
 }   // namespace
 
-int Comm::connect(uint8_t *z, size_t z_bytes, const int32_t *recv_pos_dev, const int32_t *send_pos_dev, const HaloPlan &halo,
-                  int ncol_, size_t gsum_doubles, cudaStream_t s) {
-  (void) z_bytes; (void) send_pos_dev;
+int Comm::alloc_arena(size_t z_bytes_, size_t recv_count_, size_t gsum_doubles, cudaStream_t s) {
+  auto up = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+  z_bytes = z_bytes_; recv_count = recv_count_;
+  gsum_stride = (gsum_doubles + 1) & ~(size_t) 1;
+  off_recv = up(4096 + 2 * gsum_stride * sizeof(double));
+  off_z = up(off_recv + recv_count * sizeof(int32_t));
+  arena_bytes = up(off_z + z_bytes);
+  CKC(cudaMalloc((void **) &arena, arena_bytes));
+  CKC(cudaMemsetAsync(arena, 0, arena_bytes, s));
+  CKC(cudaMalloc((void **) &counters, sizeof(uint32_t) * (2 * (size_t) world + 2)));
+  CKC(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (2 * (size_t) world + 2), s));
+  return BSB200_OK;
+}
+
+int Comm::connect(const HaloPlan &halo, int ncol_, cudaStream_t s) {
   if (transport != PEER) return BSB200_OK;
+  if (!arena) return fail(BSB200_ERR_INVALID, "connect() before alloc_arena()");
   ncol = ncol_;
   const int W = world;
   const size_t n_off = (size_t) ncol * W + 1;
   if (sizeof(ConnectHead) + n_off * sizeof(int32_t) > ShmRendezvous::kSlot)
     return fail(BSB200_ERR_UNSUPPORTED, "%d colours x %d ranks exceed the rendezvous slot", ncol, W);
-  gsum_stride = (gsum_doubles + 1) & ~(size_t) 1;
-  window_bytes = 4096 + 2 * gsum_stride * sizeof(double);
-  CKC(cudaMalloc((void **) &window, window_bytes));
-  CKC(cudaMemsetAsync(window, 0, window_bytes, s));
   const uint32_t magic = 0xB5B20000u + (uint32_t) rank;
-  CKC(cudaMemcpyAsync(window + 4092, &magic, 4, cudaMemcpyHostToDevice, s));
-  CKC(cudaMalloc((void **) &counters, sizeof(uint32_t) * (2 * (size_t) W + 2)));
-  CKC(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * (2 * (size_t) W + 2), s));
-  CKC(cudaStreamSynchronize(s));
+  CKC(cudaMemcpyAsync(arena + 4092, &magic, 4, cudaMemcpyHostToDevice, s));
+  CKC(cudaStreamSynchronize(s));   // the labels and the receive list the chain placed in the arena are there, too
 
   std::vector<unsigned char> msg(sizeof(ConnectHead) + n_off * sizeof(int32_t)), all(msg.size() * (size_t) W);
   ConnectHead head{};
-  CKC(cudaIpcGetMemHandle(&head.h_window, window));
-  CKC(cudaIpcGetMemHandle(&head.h_z, z));
-  head.has_recv = recv_pos_dev != nullptr && halo.recv_total() > 0;
-  if (head.has_recv) CKC(cudaIpcGetMemHandle(&head.h_recv, (void *) recv_pos_dev));
-  head.window_magic = magic;
+  CKC(cudaIpcGetMemHandle(&head.handle, arena));
+  int rc = allocation_offset(arena, &head.base_off);
+  if (rc) return rc;
+  head.off_recv = off_recv; head.off_z = off_z; head.arena_bytes = arena_bytes;
+  head.magic = magic;
   head.n_off = (int32_t) n_off;
   head.recv_total = (int32_t) halo.recv_total();
+  head.rank = rank;
   std::memcpy(msg.data(), &head, sizeof(head));
   std::memcpy(msg.data() + sizeof(head), halo.recv_off.data(), n_off * sizeof(int32_t));
-  int rc = shm->allgather(msg.data(), msg.size(), all.data());
-  if (rc) return rc;
+  if ((rc = shm->allgather(msg.data(), msg.size(), all.data()))) return rc;
 
-  // map the peers this rank talks to: everyone's window (shard sums), the halo neighbours' labels and receive lists
   std::vector<HaloLeg> legs((size_t) ncol * (size_t) (W - 1));
   halo_leg_count.assign((size_t) ncol, 0);
   const size_t send_total = (size_t) halo.send_total();
   if (send_total) CKC(cudaMalloc((void **) &send_dst, sizeof(int32_t) * send_total));
+  std::vector<ConnectHead> heads((size_t) W);
   for (int p = 0; p < W; p++) {
     if (p == rank) continue;
-    ConnectHead ph;
+    ConnectHead &ph = heads[(size_t) p];
     std::memcpy(&ph, all.data() + (size_t) p * msg.size(), sizeof(ph));
     const int32_t *poff = reinterpret_cast<const int32_t *>(all.data() + (size_t) p * msg.size() + sizeof(ph));
-    if (ph.n_off != (int32_t) n_off) return fail(BSB200_ERR_INVALID, "rank %d built %d halo offsets, rank %d %d", p, ph.n_off, rank, (int) n_off);
-    CKC(cudaIpcOpenMemHandle(&peer_window[p], ph.h_window, cudaIpcMemLazyEnablePeerAccess));
+    if (ph.rank != p || ph.n_off != (int32_t) n_off)
+      return fail(BSB200_ERR_INVALID, "rank %d announced itself as rank %d with %d halo offsets (expected %d)", p, ph.rank, ph.n_off, (int) n_off);
+    CKC(cudaIpcOpenMemHandle(&peer_base[p], ph.handle, cudaIpcMemLazyEnablePeerAccess));
+    peer_arena[p] = (uint8_t *) peer_base[p] + ph.base_off;
     uint32_t seen = 0;
-    CKC(cudaMemcpy(&seen, (uint8_t *) peer_window[p] + 4092, 4, cudaMemcpyDeviceToHost));
-    if (seen != ph.window_magic) return fail(BSB200_ERR_CUDA, "mapped window of rank %d does not carry its tag", p);
-    bool neighbour = false;
-    for (int c = 0; c < ncol; c++) {
-      const size_t e = (size_t) c * W + p;
-      neighbour |= halo.send_off[e + 1] > halo.send_off[e] || halo.recv_off[e + 1] > halo.recv_off[e];
-    }
-    if (!neighbour) continue;
-    CKC(cudaIpcOpenMemHandle(&peer_z[p], ph.h_z, cudaIpcMemLazyEnablePeerAccess));
-    if (ph.has_recv) CKC(cudaIpcOpenMemHandle(&peer_recv_pos[p], ph.h_recv, cudaIpcMemLazyEnablePeerAccess));
+    CKC(cudaMemcpy(&seen, peer_arena[p] + 4092, 4, cudaMemcpyDeviceToHost));
+    if (seen != ph.magic) return fail(BSB200_ERR_CUDA, "the mapped arena of rank %d does not carry its tag (%08x)", p, seen);
     for (int c = 0; c < ncol; c++) {
       const size_t e = (size_t) c * W + p;
       const int32_t s0 = halo.send_off[e], s1 = halo.send_off[e + 1];
@@ -428,15 +450,13 @@ int Comm::connect(uint8_t *z, size_t z_bytes, const int32_t *recv_pos_dev, const
       if (r1 - r0 != s1 - s0)
         return fail(BSB200_ERR_INVALID, "halo lists of ranks %d and %d disagree for colour %d (%d vs %d)", rank, p, c, s1 - s0, r1 - r0);
       if (s1 == s0 && nrecv == 0) continue;
-      if (s1 > s0) {
-        if (!peer_recv_pos[p]) return fail(BSB200_ERR_INVALID, "rank %d exported no receive list", p);
-        CKC(cudaMemcpyAsync(send_dst + s0, (const int32_t *) peer_recv_pos[p] + r0, sizeof(int32_t) * (size_t) (s1 - s0),
-                            cudaMemcpyDefault, s));
-      }
+      if (s1 > s0)
+        CKC(cudaMemcpyAsync(send_dst + s0, reinterpret_cast<const int32_t *>(peer_arena[p] + ph.off_recv) + r0,
+                            sizeof(int32_t) * (size_t) (s1 - s0), cudaMemcpyDefault, s));
       HaloLeg L{};
-      L.peer_z = (uint8_t *) peer_z[p];
-      L.peer_flag = reinterpret_cast<uint32_t *>(peer_window[p]) + rank;
-      L.my_flag = reinterpret_cast<const uint32_t *>(window) + p;
+      L.peer_z = peer_arena[p] + ph.off_z;
+      L.peer_flag = reinterpret_cast<uint32_t *>(peer_arena[p]) + rank;
+      L.my_flag = reinterpret_cast<const uint32_t *>(arena) + p;
       L.s0 = s0; L.s1 = s1; L.nrecv = nrecv; L.peer = p;
       legs[(size_t) c * (size_t) (W - 1) + (size_t) halo_leg_count[(size_t) c]++] = L;
     }
@@ -445,9 +465,9 @@ int Comm::connect(uint8_t *z, size_t z_bytes, const int32_t *recv_pos_dev, const
   for (int i = 0; i < W - 1; i++) {
     const int p = (rank + 1 + i) % W;
     GatherLeg g{};
-    g.peer_gsum = reinterpret_cast<double *>((uint8_t *) peer_window[p] + 4096);
-    g.peer_flag = reinterpret_cast<uint32_t *>(peer_window[p]) + 64 + rank;
-    g.my_flag = reinterpret_cast<const uint32_t *>(window) + 64 + p;
+    g.peer_gsum = reinterpret_cast<double *>(peer_arena[p] + 4096);
+    g.peer_flag = reinterpret_cast<uint32_t *>(peer_arena[p]) + 64 + rank;
+    g.my_flag = reinterpret_cast<const uint32_t *>(arena) + 64 + p;
     g.peer = p;
     glegs[(size_t) i] = g;
   }
@@ -465,13 +485,13 @@ void Comm::enqueue_halo_peer(int colour, const uint8_t *z, const int32_t *send_p
   const int nlegs = halo_leg_count[(size_t) colour];
   if (nlegs == 0) return;
   k_halo_peer<<<nlegs, 256, 0, s>>>(halo_legs + (size_t) colour * (size_t) (world - 1), z, send_pos_dev, send_dst, counters,
-                                    world, err);
+                                    world, err, (unsigned long long) peer_timeout_ns);
   g_launches++;
 }
 
 void Comm::enqueue_gather_peer(size_t offset_doubles, size_t count_doubles, int *err, cudaStream_t s) {
   k_gather_peer<<<world - 1, 256, 0, s>>>(gather_legs, gsum(), gsum_stride, offset_doubles, count_doubles, counters, world,
-                                          err);
+                                          err, (unsigned long long) peer_timeout_ns);
   g_launches++;
 }
 

@@ -57,9 +57,14 @@ struct Comm {
   void *nccl = nullptr;   // ncclComm_t
   // ---- PEER
   ShmRendezvous *shm = nullptr;
-  uint8_t *window = nullptr;            // exported: [flags page | gsum parity 0 | gsum parity 1]
-  size_t window_bytes = 0, gsum_stride = 0;
-  void *peer_window[kMaxPeerWorld] = {}, *peer_z[kMaxPeerWorld] = {}, *peer_recv_pos[kMaxPeerWorld] = {};
+  // ONE exported allocation per rank: [flags page | shard sums parity 0 | parity 1 | receive list | labels].
+  // (A single handle per rank: small cudaMalloc blocks may share an underlying allocation, which can be opened
+  // only once per process and whose handle names its base, so the arena's offset in it travels with the handle.)
+  uint8_t *arena = nullptr;
+  size_t arena_bytes = 0, gsum_stride = 0, off_recv = 0, off_z = 0, recv_count = 0, z_bytes = 0;
+  void *peer_base[kMaxPeerWorld] = {};      // what cudaIpcOpenMemHandle returned (closed at shutdown)
+  uint8_t *peer_arena[kMaxPeerWorld] = {};  // the peer's arena inside that mapping
+  uint64_t peer_timeout_ns = BSB_PEER_TIMEOUT_NS;
   int32_t *send_dst = nullptr;          // for every send entry: position in the peer's label array
   HaloLeg *halo_legs = nullptr;         // [ncol][world - 1]
   GatherLeg *gather_legs = nullptr;     // [world - 1]
@@ -74,10 +79,14 @@ struct Comm {
   // host-side allgather of `bytes` per rank (set-up data: handles, offsets, column sums)
   int host_allgather(const void *mine, size_t bytes, void *all);
 
-  // PEER: export / map the buffers and build the leg tables.  gsum_doubles = G * Emax (one parity).
-  int connect(uint8_t *z, size_t z_bytes, const int32_t *recv_pos_dev, const int32_t *send_pos_dev, const HaloPlan &halo,
-              int ncol, size_t gsum_doubles, cudaStream_t s);
-  double *gsum() const { return reinterpret_cast<double *>(window + 4096); }
+  // PEER: the exported arena (labels: z_bytes, receive list: recv_count int32, shard sums: gsum_doubles = G * Emax
+  // per parity), zeroed.  The chain places its label array and receive list in it, then calls connect(), which
+  // exchanges the handles, maps the peers and builds the leg tables.
+  int alloc_arena(size_t z_bytes, size_t recv_count, size_t gsum_doubles, cudaStream_t s);
+  int connect(const HaloPlan &halo, int ncol, cudaStream_t s);
+  double *gsum() const { return reinterpret_cast<double *>(arena + 4096); }
+  int32_t *recv_pos() const { return reinterpret_cast<int32_t *>(arena + off_recv); }
+  uint8_t *z() const { return arena + off_z; }
   const uint32_t *gather_epoch() const { return counters + 2 * world; }
 
   // PEER data path
