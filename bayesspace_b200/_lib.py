@@ -66,7 +66,7 @@ EXPORTS = [
     "bsb200_subspot_neighbors", "bsb200_neighbors_to_matrix4", "bsb200_colour_graph", "bsb200_colour_lattice",
     "bsb200_cluster", "bsb200_comm_unique_id", "bsb200_shard_plan", "bsb200_chain_create", "bsb200_chain_run", "bsb200_chain_profile", "bsb200_chain_state",
     "bsb200_chain_destroy", "bsb200_kernel_launches", "bsb200_eval_loglik", "bsb200_eval_suffstats",
-    "bsb200_chain_dry_sweep", "bsb200_debug_rng", "bsb200_deconv",
+    "bsb200_chain_dry_sweep", "bsb200_debug_rng", "bsb200_debug_rendezvous", "bsb200_deconv",
 ]
 
 _lib = None

@@ -109,10 +109,26 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
 }
 
 int choose_groups(int64_t n) { return n >= 262144 ? kGroups : 1; }
-int choose_segment(int64_t n) {
-  // tiles per segment: a function of n only (the fold order, hence the bits of a chain, depends on it)
+int choose_segment(int64_t n, int ncol) {
+  // Tiles per segment (= per CTA of a sweep launch): a function of the GLOBAL problem only (n, colours), never of
+  // the GPU count, because the fold order -- hence the bits of a chain -- depends on it.
   int64_t tps = n / ((int64_t) kBlock * 2048);
   tps = std::max<int64_t>(1, std::min<int64_t>(8, tps));
+  if (choose_groups(n) == kGroups && ncol > 0) {
+    // Sharded sizes: a colour phase of W ranks launches (kGroups / W) * ceil(tiles / t) CTAs onto 148 SMs x 4 resident
+    // CTAs; its time is about waves * t.  Pick the t whose wave quantisation loss, summed over W = 1, 2, 4, 8, is
+    // smallest (at 10M spots: t = 9 -> 8 / 4 / 2 / 1 full waves instead of 9 / 5 / 3 / 2 with t = 8).
+    const int64_t slots = 148 * 4;
+    const int64_t tiles = ((n / kGroups + ncol - 1) / ncol + kBlock - 1) / kBlock;   // per (shard, colour)
+    int64_t best = 0, best_cost = 0;
+    for (int64_t t = 6; t <= 12; t++) {
+      const int64_t segs = (tiles + t - 1) / t;
+      int64_t cost = 0;
+      for (int W = 1; W <= 8; W *= 2) cost += ((kGroups / W * segs + slots - 1) / slots) * t * W;
+      if (best == 0 || cost < best_cost) { best = t; best_cost = cost; }
+    }
+    tps = best;
+  }
   if (const char *e = getenv("BSB200_SEG_TILES")) tps = std::max(1, atoi(e));   // tuning knob
   return (int) tps * kBlock;
 }
@@ -363,7 +379,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if (rc) return rc;
   }
   mark("colouring");
-  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n), plan.g0, plan.g1, plan.lo, plan.hi);
+  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol), plan.g0, plan.g1, plan.lo, plan.hi);
   const SpotOrder &ord = ch->ord;
   mark("spot order");
   if (world > 1) {

@@ -50,7 +50,7 @@ struct SpotOrder {
 
 int select_device(int device);
 int choose_groups(int64_t n);
-int choose_segment(int64_t n);
+int choose_segment(int64_t n, int ncol = 0);   // ncol = 0: the plain n-based rule (probes, deconvolution)
 void param_kernel_init();
 
 }   // namespace bsb

@@ -521,6 +521,25 @@ int Comm::exchange_u8(const uint8_t *sendbuf, const int32_t *send_off, uint8_t *
 
 }   // namespace bsb
 
+// Host rendezvous alone (no GPU): `rounds` allgathers of `bytes` per rank; round r sends mine[i] + r.  Test hook.
+extern "C" int bsb200_debug_rendezvous(const void *id128, int32_t world, int32_t rank, const uint8_t *mine, int64_t bytes,
+                                       int32_t rounds, uint8_t *all_last) {
+  using namespace bsb;
+  if (!id128 || !mine || !all_last || world < 1 || world > kMaxPeerWorld || rank < 0 || rank >= world || bytes < 1)
+    return fail(BSB200_ERR_INVALID, "Invalid arguments!");
+  if (std::memcmp(id128, kPeerMagic, 8) != 0) return fail(BSB200_ERR_INVALID, "not a peer-transport communicator id");
+  ShmRendezvous shm;
+  int rc = shm.open((const unsigned char *) id128 + 8, world, rank);
+  if (rc) return rc;
+  std::vector<uint8_t> msg((size_t) bytes), all((size_t) bytes * (size_t) world);
+  for (int r = 0; r < rounds; r++) {
+    for (int64_t i = 0; i < bytes; i++) msg[(size_t) i] = (uint8_t) (mine[i] + r);
+    if ((rc = shm.allgather(msg.data(), (size_t) bytes, all.data()))) return rc;
+  }
+  std::memcpy(all_last, all.data(), all.size());
+  return BSB200_OK;
+}
+
 extern "C" int bsb200_comm_unique_id(void *id128) {
   if (!id128) return bsb::fail(BSB200_ERR_INVALID, "Invalid arguments!");
   return bsb::comm_unique_id(id128);

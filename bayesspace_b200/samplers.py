@@ -95,6 +95,16 @@ def comm_unique_id():
     return bytes(buf)
 
 
+def debug_rendezvous(comm_id, world, rank, mine, rounds=1):
+    """Host rendezvous of the peer transport alone (CPU): returns the (world, len(mine)) bytes of the last round."""
+    mine = np.ascontiguousarray(mine, dtype=np.uint8)
+    out = np.zeros((world, mine.size), dtype=np.uint8)
+    idb = np.frombuffer(comm_id, dtype=np.uint8).copy()
+    check(lib().bsb200_debug_rendezvous(ptr(idb), int(world), int(rank), ptr(mine), C.c_int64(mine.size), int(rounds),
+                                        ptr(out)))
+    return out
+
+
 def shard_plan(df_j, colour, ncolours, groups, world, rank):
     """Host-only view of one rank's share of a sharded chain: own range, ghost ids, halo lists (original ids)."""
     p, idx = neighbors.as_csr(df_j)

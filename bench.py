@@ -10,8 +10,10 @@ metric -- is defined.  C2 (Visium, 4,992 spots) and C4 (700k bins) are reported 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c2] [--impl reference]
 
 N > 1 is launched by the driver through torch.distributed.run, one rank per GPU: ONE chain is spot-sharded over
-the N GPUs in row strips (labels of boundary spots exchanged after every colour phase, per-shard statistics
-allgathered once per iteration, both on NCCL inside the captured graph): total work fixed, "scaling": "strong".
+the N GPUs in row strips (labels of boundary spots stored into the neighbour GPUs' ghost slots after every colour
+phase, per-shard statistics stored into every peer once per iteration, both by the library's own kernels over
+NVLink peer memory inside the captured graph; BSB200_COMM=nccl selects the NCCL send/recv + allgather baseline):
+total work fixed, "scaling": "strong".
 The sharded chain is bit-identical to the 1-GPU chain (tests/mgpu_check.py).  `--replicas` runs one independent
 chain per GPU instead (the qTune / multi-chain mode: no data-path collective, weak scaling).
 """
@@ -378,8 +380,10 @@ def run_gpu(args):
             "scaling": "weak" if (world > 1 and not sharded) else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(w, args.workload, parallelism=(
-                "one chain spot-sharded over %d GPUs in row strips (halo labels + allgather of shard statistics on NCCL)"
-                % world if sharded else ("1 chain per GPU (replicas, no collective)" if world > 1 else "single chain, 1 GPU")),
+                "one chain spot-sharded over %d GPUs in row strips; halo labels and shard statistics travel as %s"
+                % (world, "NCCL send/recv + allgather" if os.environ.get("BSB200_COMM") == "nccl" else
+                   "stores into peer GPU memory from the library's own kernels (CUDA IPC over NVLink, epoch flags)")
+                if sharded else ("1 chain per GPU (replicas, no collective)" if world > 1 else "single chain, 1 GPU")),
                 sweeps_per_s=(1 if sharded or world == 1 else world) * K / (ms * 1e-3), colours=colour[1]),
             "roofline": {"bound": "hbm", "kernel": "k_sweep<%d,t,shared>" % w.d, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(args.workload),

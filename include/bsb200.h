@@ -203,6 +203,12 @@ int bsb200_eval_suffstats(int32_t device, const double *Y, int64_t n, int32_t d,
 int bsb200_chain_dry_sweep(bsb200_chain *chain, int32_t *z_new, double *w_new, double *h_prev,
                            double *h_new, double *prob, int32_t *accepted);
 
+/* Test hook for the host rendezvous of the peer transport (no GPU involved): `rounds` allgathers of `bytes` bytes
+ * per rank through the shared-memory segment named by a peer-transport id; in round r rank p contributes mine[i] + r.
+ * all_last (world * bytes) receives the last round. */
+int bsb200_debug_rendezvous(const void *id128, int32_t world, int32_t rank, const uint8_t *mine, int64_t bytes,
+                            int32_t rounds, uint8_t *all_last);
+
 /* Keyed random variates exactly as the kernels draw them (u in (0,1), N(0,1), Gamma(shape, scale)):
  * kind 0 uniform pair (count must be 2), 1 normals m0.., 2 gammas for index0.. */
 int bsb200_debug_rng(int32_t device, int32_t kind, uint64_t seed, uint32_t purpose, uint32_t index,

@@ -29,9 +29,33 @@ def split(plan, key, ncol, W):
     return out
 
 
+def check_rendezvous(rank, W):
+    """The peer transport's host rendezvous (POSIX shared memory named by the communicator id): several rounds of
+    allgather across real processes, with ranks arriving at different times."""
+    import time
+    os.environ.pop("BSB200_COMM", None)
+    ids = [samplers.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    assert ids[0][:8] == b"BSBPEER1"
+    mine = (np.arange(1000) * (rank + 3) % 251).astype(np.uint8)
+    time.sleep(0.2 * rank)
+    got = samplers.debug_rendezvous(ids[0], W, rank, mine, rounds=5)
+    for p in range(W):
+        expect = ((np.arange(1000) * (p + 3) % 251) + 4).astype(np.uint8)
+        assert np.array_equal(got[p], expect), (rank, p)
+    # a second communicator in the same processes gets its own segment
+    ids = [samplers.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    got = samplers.debug_rendezvous(ids[0], W, rank, np.full(7, rank, np.uint8), rounds=1)
+    assert np.array_equal(got, np.repeat(np.arange(W, dtype=np.uint8)[:, None], 7, axis=1))
+    if rank == 0:
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith("bsb200-")], "rendezvous segment left behind"
+
+
 def main():
     dist.init_process_group("gloo")
     rank, W = dist.get_rank(), dist.get_world_size()
+    check_rendezvous(rank, W)
     for name, groups in (("small_sq", 8), ("small_hex", 64)):
         w = synth.make_workload(name)
         _, csr = B.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
