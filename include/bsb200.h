@@ -149,10 +149,16 @@ typedef struct bsb200_cluster_out {
 
 int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out);
 
-/* Multi-GPU (one process per GPU): rank 0 creates the communicator id, the host layer hands the 128 bytes to
- * every rank (torch.distributed broadcast in bench.py), each rank passes them in bsb200_cluster_args.comm_id.
- * Per iteration the ranks exchange the labels of boundary spots after every colour phase and allgather the
- * per-shard statistics; there is no reference counterpart (the reference is single-process). */
+/* Multi-GPU (one process per GPU of one box): rank 0 creates the communicator id, the host layer hands the 128
+ * bytes to every rank (torch.distributed broadcast in bench.py), each rank passes them in
+ * bsb200_cluster_args.comm_id; ONE id per sharded chain / bsb200_cluster call.  Per iteration the ranks exchange
+ * the labels of boundary spots after every colour phase and the per-shard statistics once.  The id selects the
+ * transport: by default the library's own kernels store into peer GPU memory over NVLink (CUDA IPC mappings,
+ * epoch flags, host rendezvous in POSIX shared memory); with BSB200_COMM=nccl in rank 0's environment when the
+ * id is made, NCCL send/recv + allgather (libnccl.so.2 bound at run time).  Both give the same bits.
+ * Environment knobs: BSB200_PEER_TIMEOUT (s, default 20: how long a kernel waits for a peer's flag before the
+ * chain fails with BSB200_ERR_CUDA), BSB200_RENDEZVOUS_TIMEOUT (s, default 120: host-side wait for the other
+ * ranks at set-up).  There is no reference counterpart (the reference is single-process). */
 int bsb200_comm_unique_id(void *id128);
 /* Host-only view of a rank's share of a sharded chain (own range, ghost spots, halo lists); for tests. */
 int bsb200_shard_plan(const int64_t *ptr, const int32_t *idx, int64_t n, const int32_t *colour, int32_t ncolours,
