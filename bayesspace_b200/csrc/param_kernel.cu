@@ -97,77 +97,64 @@ __device__ __forceinline__ void blk_inv_upper(int off_U, int off_T, int off_rd, 
 
 // ---- register-resident warp versions (one warp per matrix, lane k owns column k) ----------------------
 // The shared-memory versions above cost ~3,000 cycles per elimination step (dependent LDS -> DFMA -> STS
-// chains); with the column of every lane in registers a step is one rsqrt and j broadcasts (SHFL), which
-// makes these ~10x faster.  DM = d rounded up to 8, 16, 24 or 32; loops are fully unrolled so that every
-// register index is static, steps with j >= d are skipped (uniform predicate).
-template <int DM>
-__device__ __forceinline__ void warp_revchol_reg(double *U, int d, int lane, int *ok) {
-  double c[DM];
+// chains); with the column of every lane in registers a step is one rsqrt, one column published to shared
+// memory by its owner and j broadcast loads, which makes these ~10x faster.  D = d exactly (1..16): every loop
+// is fully unrolled with static register indices and no run-time bound, which keeps the code small -- the kernel
+// runs once per iteration between sweeps that flush L2, so its instructions are fetched from HBM every time
+// (the first version, unrolled for DM = 16 with run-time d, was 445 KB of SASS and twice as slow at 10M spots
+// as at 5k spots for that reason alone).
+template <int D>
+__device__ __forceinline__ void warp_revchol_reg(double *U, int lane, int *ok) {
+  double c[D];   // column `lane`, rows 0..lane; entries below the diagonal are never read (don't care)
 #pragma unroll
-  for (int i = 0; i < DM; i++) c[i] = (lane < d && i <= lane) ? U[lane * d + i] : 0.0;
+  for (int i = 0; i < D; i++) c[i] = (lane < D && i <= lane) ? U[lane * D + i] : 0.0;
 #pragma unroll
-  for (int j = DM - 1; j >= 0; j--) {
-    if (j >= d) continue;
-    const double ajj = __shfl_sync(0xffffffffu, c[j], j);
-    if (!(ajj > 0.0)) *ok = 0;
-    const double r = rsqrt(ajj);
-    double ukj = 0.0;   // u_kj of this lane's own column k = lane
+  for (int j = D - 1; j >= 0; j--) {
+    if (lane == j) {   // column j is final: u_ij = a_ij / sqrt(a_jj), stored where the result lives anyway
+      const double ajj = c[j];
+      if (!(ajj > 0.0)) *ok = 0;
+      const double r = rsqrt(ajj);
 #pragma unroll
-    for (int i = 0; i < j; i++) {
-      const double uij = __shfl_sync(0xffffffffu, c[i], j) * r;
-      if (i == lane) ukj = uij;
+      for (int i = 0; i < j; i++) U[j * D + i] = c[i] * r;
+      U[j * D + j] = ajj * r;
     }
+    __syncwarp();
+    if (j > 0) {
+      const double ukj = lane < j ? U[j * D + lane] : 0.0;   // u_kj of this lane's own column k = lane
 #pragma unroll
-    for (int i = 0; i < j; i++) {
-      const double uij = __shfl_sync(0xffffffffu, c[i], j) * r;   // column j is still unscaled in lane j
-      if (lane < j && i <= lane) c[i] = fma(-uij, ukj, c[i]);
-    }
-    if (lane == j) {
-#pragma unroll
-      for (int i = 0; i < j; i++) c[i] *= r;
-      c[j] = ajj * r;
+      for (int i = 0; i < j; i++) c[i] = fma(-U[j * D + i], ukj, c[i]);   // broadcast loads; lanes >= j: ukj = 0
     }
   }
-#pragma unroll
-  for (int i = 0; i < DM; i++)
-    if (lane < d && i < d) U[lane * d + i] = i <= lane ? c[i] : 0.0;
+  __syncwarp();
 }
 
 // T = U^-1 (upper), row by row from the bottom; U and T in shared memory (may not alias).
-template <int DM>
-__device__ __forceinline__ void warp_inv_upper_reg(const double *U, double *T, int d, int lane) {
-  double c[DM], t[DM];
-  double dg = 1.0;
+template <int D>
+__device__ __forceinline__ void warp_inv_upper_reg(const double *U, double *T, int lane) {
+  double t[D];   // column `lane` of T; t[k] = 0 for k > lane, so the sums below need no predicate
+  if (lane < D) T[lane * D + lane] = 1.0 / U[lane * D + lane];   // reciprocal diagonals, read back as broadcasts
+  __syncwarp();
 #pragma unroll
-  for (int i = 0; i < DM; i++) {
-    c[i] = (lane < d && i <= lane) ? U[lane * d + i] : 0.0;
-    t[i] = 0.0;
-    if (i == lane && lane < d) dg = c[i];
-  }
-  const double rdg = 1.0 / dg;
-#pragma unroll
-  for (int i = DM - 1; i >= 0; i--) {
-    if (i >= d) continue;
+  for (int i = D - 1; i >= 0; i--) {
     double s = lane == i ? 1.0 : 0.0;
 #pragma unroll
-    for (int k = i + 1; k < DM; k++) {
-      if (k >= d) continue;
-      const double uik = __shfl_sync(0xffffffffu, c[i], k);   // U[i,k] lives in lane k
-      if (k <= lane) s = fma(-uik, t[k], s);
-    }
-    const double ri = __shfl_sync(0xffffffffu, rdg, i);
-    t[i] = lane >= i ? s * ri : 0.0;
+    for (int k = i + 1; k < D; k++) s = fma(-U[k * D + i], t[k], s);   // broadcast loads of U[i,k]
+    t[i] = lane >= i ? s * T[i * D + i] : 0.0;
   }
+  __syncwarp();
 #pragma unroll
-  for (int i = 0; i < DM; i++)
-    if (lane < d && i < d) T[lane * d + i] = i <= lane ? t[i] : 0.0;
+  for (int i = 0; i < D; i++)
+    if (lane < D) T[lane * D + i] = i <= lane ? t[i] : 0.0;
 }
 
-template <int DM>
+// D = exact dimension 1..16 (register path) or 0 (run-time d up to 32, shared-memory path)
+template <int D>
 __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, int batch) {
   extern __shared__ double sm[];
   __shared__ int s_ok;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  // d stays a run-time value outside the factorisations: compile-time d would fully unroll every small loop below
+  // (+120 KB of code that is fetched from HBM once per iteration for nothing)
   const int d = a.PL.d, q = a.PL.q, nl = a.PL.nl, np = a.PL.np, E = a.SL.E;
   const int dd = d * d;
   const Key key{a.key0, a.key1};
@@ -246,11 +233,11 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       MA[idx] = i <= j ? a.lambda0[e] + st[a.SL.nk + k] * l : 0.0;                      // upper triangle of P_k
     }
     __syncthreads();
-    if (DM <= 16) {
+    if constexpr (D > 0) {
+#pragma unroll 1   // one copy of the unrolled factorisations, not four
       for (int b = warp; b < nb; b += 8) {
-        warp_revchol_reg<DM>(MA + b * dd, d, lane, &s_ok);            // MA = U
-        __syncwarp();
-        warp_inv_upper_reg<DM>(MA + b * dd, MB + b * dd, d, lane);    // MB = R = chol_upper(var)
+        warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);            // MA = U
+        warp_inv_upper_reg<D>(MA + b * dd, MB + b * dd, lane);    // MB = R = chol_upper(var)
       }
       __syncthreads();
     } else {
@@ -313,13 +300,15 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       MC[idx] = av;
     }
     __syncthreads();
-    if (DM <= 16) {
+    BSB_T(6);
+    if constexpr (D > 0) {
+#pragma unroll 1   // one copy of the unrolled factorisations, not four
       for (int b = warp; b < nb; b += 8) {
-        warp_revchol_reg<DM>(MA + b * dd, d, lane, &s_ok);            // V + S = U U^T
-        __syncwarp();
-        warp_inv_upper_reg<DM>(MA + b * dd, MB + b * dd, d, lane);    // MB = C = chol_upper((V + S)^-1)
+        warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);            // V + S = U U^T
+        warp_inv_upper_reg<D>(MA + b * dd, MB + b * dd, lane);    // MB = C = chol_upper((V + S)^-1)
       }
       __syncthreads();
+    BSB_T(7);
     } else {
       blk_revchol((int) (MA - sm), nb, d, &s_ok);
       blk_inv_upper((int) (MA - sm), (int) (MB - sm), (int) (va - sm), nb, d);
@@ -331,6 +320,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       MD[idx] = s;
     }
     __syncthreads();
+    BSB_T(8);
     for (int idx = tid; idx < nb * (int) dd; idx += nt) {   // Lambda = B^T B -> MB (full), MA (upper triangle)
       const int b = idx / (int) dd, e = idx - b * (int) dd, i = e % d, j = e / d, kk = k0 + b;
       const int k1 = i < j ? i : j;
@@ -342,9 +332,12 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       MA[idx] = i <= j ? s : 0.0;
     }
     __syncthreads();
-    if (DM <= 16) {
-      for (int b = warp; b < nb; b += 8) warp_revchol_reg<DM>(MA + b * dd, d, lane, &s_ok);   // Lambda = rooti rooti^T
+    BSB_T(9);
+    if constexpr (D > 0) {
+#pragma unroll 1
+      for (int b = warp; b < nb; b += 8) warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);   // Lambda = rooti rooti^T
       __syncthreads();
+    BSB_T(10);
     } else {
       blk_revchol((int) (MA - sm), nb, d, &s_ok);
     }
@@ -369,6 +362,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       if (lane == 0) P[a.PL.logdet + k0 + b] = ld;
     }
     __syncthreads();
+    BSB_T(11);
     // derived per-cluster vectors: g = M mu, gL = Lambda mu (then c = mu^T g, cL = mu^T gL)
     const int c0 = a.vvv ? k0 : 0, c1 = a.vvv ? k0 + nb : q;
     for (int idx = tid; idx < (c1 - c0) * d; idx += nt) {
@@ -385,6 +379,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       P[a.PL.gL + k * d + i] = s1;
     }
     __syncthreads();
+    BSB_T(12);
     for (int k = c0 + tid; k < c1; k += nt) {
       double s0 = 0.0, s1 = 0.0;
       for (int i = 0; i < d; i++) { s0 += mu_s[k * d + i] * va[k * d + i]; s1 += mu_s[k * d + i] * vb[k * d + i]; }
@@ -392,6 +387,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       P[a.PL.cL + k] = s1;
     }
     __syncthreads();
+    BSB_T(13);
   }
   BSB_T(4);
   if (tid == 0 && !s_ok) atomicExch(a.err, BSB_DEVERR_NUMERIC);
@@ -412,6 +408,14 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
 
 static const size_t kParamSmemMax = 220 * 1024;
 
+typedef void (*param_kernel_t)(ParamArgs, int, int);
+static param_kernel_t *param_kernel_table() {
+  static param_kernel_t t[17] = {k_param<0>,  k_param<1>,  k_param<2>,  k_param<3>,  k_param<4>,  k_param<5>,
+                                 k_param<6>,  k_param<7>,  k_param<8>,  k_param<9>,  k_param<10>, k_param<11>,
+                                 k_param<12>, k_param<13>, k_param<14>, k_param<15>, k_param<16>};
+  return t;
+}
+
 void launch_param(const ParamArgs &a, cudaStream_t stream) {
   const int d = a.PL.d, q = a.PL.q;
   const size_t per_mat = 4 * (size_t) d * d * sizeof(double);
@@ -422,10 +426,9 @@ void launch_param(const ParamArgs &a, cudaStream_t stream) {
   int batch = (int) std::min<size_t>((size_t) want, avail / per_mat);
   if (batch < 1) batch = 1;
   const size_t smem = base + (stats_in_smem ? stats_bytes : 0) + (size_t) batch * per_mat;
-  // d <= 16: factorisations with one register-resident column per lane; larger d: shared-memory versions
-  if (d <= 8) k_param<8><<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
-  else if (d <= 16) k_param<16><<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
-  else k_param<32><<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
+  // d <= 16: factorisations with one register-resident column per lane (kernel instantiated for the exact d);
+  // larger d: shared-memory versions with run-time d
+  param_kernel_table()[d <= 16 ? d : 0]<<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
 }
 
 #ifdef BSB_PARAM_TIMING
@@ -435,9 +438,8 @@ extern "C" int bsb200_debug_param_timing(long long *out16) {
 #endif
 
 void param_kernel_init() {
-  cudaFuncSetAttribute(k_param<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
-  cudaFuncSetAttribute(k_param<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
-  cudaFuncSetAttribute(k_param<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
+  for (int i = 0; i <= 16; i++)
+    cudaFuncSetAttribute(param_kernel_table()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
 }
 
 }   // namespace bsb
