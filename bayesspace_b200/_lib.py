@@ -39,7 +39,8 @@ class ClusterArgs(C.Structure):
 class ClusterOut(C.Structure):
     _fields_ = [("z", C.c_void_p), ("mu", C.c_void_p), ("lambda_", C.c_void_p), ("weights", C.c_void_p),
                 ("plogLik", C.c_void_p), ("rows_done", C.c_int32), ("ncolours", C.c_int32),
-                ("setup_ms", C.c_double), ("device_ms", C.c_double), ("own_lo", C.c_int64), ("own_hi", C.c_int64)]
+                ("setup_ms", C.c_double), ("device_ms", C.c_double), ("own_lo", C.c_int64), ("own_hi", C.c_int64),
+                ("z_mode", C.c_void_p), ("mode_from", C.c_int32)]
 
 
 class DeconvArgs(C.Structure):
@@ -54,7 +55,8 @@ class DeconvArgs(C.Structure):
 
 class DeconvOut(C.Structure):
     _fields_ = [("z", C.c_void_p), ("mu", C.c_void_p), ("lambda_", C.c_void_p), ("weights", C.c_void_p),
-                ("Y", C.c_void_p), ("Y_mean", C.c_void_p), ("mean_from", C.c_int32), ("Ychange", C.c_void_p),
+                ("Y", C.c_void_p), ("Y_mean", C.c_void_p), ("mean_from", C.c_int32), ("mode_from", C.c_int32),
+                ("z_mode", C.c_void_p), ("Ychange", C.c_void_p),
                 ("plogLik", C.c_void_p), ("df_j", C.c_void_p), ("rows_done", C.c_int32), ("ncolours", C.c_int32),
                 ("setup_ms", C.c_double), ("device_ms", C.c_double)]
 

@@ -165,7 +165,7 @@ struct bsb200_chain {
   DevBuf<double> Y, w, params, partials, gsum, stats, T_fixed, mu0c, lambda0, lm0, ybar, plogLik, snap_mu, snap_lambda, snap_w;
   DevBuf<uint8_t> z, halo_send, halo_recv;
   DevBuf<int32_t> ell, orig, seg_begin, seg_count, seg_slot, group_start, snap_z, send_pos, recv_pos;
-  DevBuf<uint32_t> iter;
+  DevBuf<uint32_t> iter, mode_cnt, mode_first;   // mode_*: q x n_own label histogram of the kept snapshots
   DevBuf<int> err;
   std::vector<double> ybar_host;
   int32_t *h_snap_z = nullptr;   // pinned staging of one snapshot
@@ -583,10 +583,22 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     remaining -= run;
     const bool boundary = (ch->iters_done + 1) % ch->thin == 0;
     if (boundary) {
-      launch_snapshot(ch->z.p, ch->tdist ? ch->w.p : nullptr, ch->orig.p, ch->n_own, ch->snap_z.p,
-                      ch->tdist ? ch->snap_w.p : nullptr, s, ch->lo);
-      CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
-      if (ch->tdist) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
+      const int64_t row = (ch->iters_done + 1) / ch->thin;
+      const bool want_w = ch->tdist && (!out || out->weights);
+      launch_snapshot(ch->z.p, want_w ? ch->w.p : nullptr, ch->orig.p, ch->n_own, ch->snap_z.p,
+                      want_w ? ch->snap_w.p : nullptr, s, ch->lo);
+      if (out && out->z_mode && row >= out->mode_from && row < ch->nrep / ch->thin + 1) {
+        if (!ch->mode_cnt.p) {
+          int rc;
+          if ((rc = ch->mode_cnt.alloc((size_t) ch->q * ch->n_own)) || (rc = ch->mode_first.alloc((size_t) ch->q * ch->n_own)))
+            return rc;
+          CK(cudaMemsetAsync(ch->mode_cnt.p, 0, sizeof(uint32_t) * ch->q * ch->n_own, s));
+        }
+        launch_mode_accumulate(ch->snap_z.p, ch->n_own, ch->q, (uint32_t) row, ch->mode_cnt.p, ch->mode_first.p, s);
+      }
+      // the snapshots travel to the host only when the caller asked for the matrices
+      if (!out || out->z) CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
+      if (want_w) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ch->ev1, s));
     CK(cudaStreamSynchronize(s));
@@ -620,6 +632,14 @@ int chain_finish_impl(bsb200_chain *ch, bsb200_cluster_out *out) {
   if (out->plogLik) CK(cudaMemcpyAsync(out->plogLik, ch->plogLik.p, sizeof(double) * ch->nrep, cudaMemcpyDeviceToHost, s));
   if (out->mu) CK(cudaMemcpyAsync(out->mu, ch->snap_mu.p, sizeof(double) * nsnap * q * d, cudaMemcpyDeviceToHost, s));
   if (out->lambda) CK(cudaMemcpyAsync(out->lambda, ch->snap_lambda.p, sizeof(double) * nsnap * ch->nl * d * d, cudaMemcpyDeviceToHost, s));
+  if (out->z_mode) {
+    if (ch->mode_cnt.p) {   // mode of the kept label snapshots, written for the rank's own spots
+      launch_mode_final(ch->mode_cnt.p, ch->mode_first.p, ch->n_own, q, ch->snap_z.p, s);
+      CK(cudaMemcpyAsync(out->z_mode + ch->lo, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
+    } else {
+      std::memset(out->z_mode + ch->lo, 0, sizeof(int32_t) * ch->n_own);   // no row reached mode_from
+    }
+  }
   CK(cudaStreamSynchronize(s));
   if (ch->comm_rc) return ch->comm_rc;
   return BSB200_OK;
@@ -773,13 +793,17 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   std::unique_ptr<bsb200_chain> guard(ch);
   const int64_t n = args->n;
   const int d = args->d, q = args->q, nsnap = args->nrep / args->thin + 1, nl = ch->nl;
-  // row 0 of every output = initial state (src/cluster.cpp:232-237, 462-469); later rows zero until written
+  // row 0 of every output = initial state (src/cluster.cpp:232-237, 462-469); rows the chain does not reach stay
+  // zero as in the reference.  Single GPU: every later row is overwritten in full by its snapshot, so only the rows
+  // of an interrupted run are zeroed (at the end) -- a second pass over 1.3 GB of host memory at 10M spots otherwise.
+  // Sharded: a rank writes its own columns only, the others are zeroed up front.
+  const bool sharded = ch->world() > 1;
   if (out->z) {
-    std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
+    if (sharded) std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
     std::memcpy(out->z, args->init, sizeof(int32_t) * n);
   }
   if (out->weights && ch->tdist) {
-    std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
+    if (sharded) std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
     for (int64_t j = 0; j < n; j++) out->weights[j] = 1.0;
   }
   out->rows_done = 1;
@@ -790,6 +814,11 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   double ms = 0.0;
   rc = chain_run_impl(ch, args->nrep - 1, out, &ms, true);
   out->device_ms = ms;
+  if (!sharded && out->rows_done < nsnap) {   // interrupted (or failed) run: the rows never reached read as zero
+    const size_t r0 = (size_t) out->rows_done, nr = (size_t) (nsnap - out->rows_done);
+    if (out->z) std::memset(out->z + r0 * n, 0, sizeof(int32_t) * nr * n);
+    if (out->weights && ch->tdist) std::memset(out->weights + r0 * n, 0, sizeof(double) * nr * n);
+  }
   if (rc && rc != BSB200_ERR_CANCELLED) return rc;
   int rc2 = chain_finish_impl(ch, out);
   if (rc2) return rc2;

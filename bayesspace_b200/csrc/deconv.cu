@@ -168,6 +168,8 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
       (rc = iter.alloc(1)) || (rc = err.alloc(1)) || (rc = nacc.alloc((size_t) ld0)))
     return rc;
   if (out->Y_mean && (rc = Ymean.alloc((size_t) n * d))) return rc;
+  DevBuf<uint32_t> mode_cnt, mode_first;   // q x n label histogram of the kept snapshots
+  if (out->z_mode && ((rc = mode_cnt.alloc((size_t) q * n)) || (rc = mode_first.alloc((size_t) q * n)))) return rc;
   if (adaptive) {
     if ((rc = A.alloc((size_t) np * S * ld0))) return rc;
     std::vector<double> Ah((size_t) np * S * ld0, 0.0);
@@ -190,6 +192,7 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
   CK(cudaMemsetAsync(snap_mu.p, 0, sizeof(double) * nsnap * q * d, s));
   CK(cudaMemsetAsync(snap_lambda.p, 0, sizeof(double) * nsnap * d * d, s));
   if (out->Y_mean) CK(cudaMemsetAsync(Ymean.p, 0, sizeof(double) * n * d, s));
+  if (out->z_mode) CK(cudaMemsetAsync(mode_cnt.p, 0, sizeof(uint32_t) * q * n, s));
 
   auto deconv_args = [&](int colour_id, int stats_only) {
     DeconvArgs k{};
@@ -297,6 +300,8 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
         mean_count++;
         launch_running_mean(snap_Y.p, Ymean.p, n * d, 1.0 / mean_count, s);
       }
+      if (out->z_mode && (int) r >= out->mode_from && r < (size_t) nsnap)
+        launch_mode_accumulate(snap_z.p, n, q, (uint32_t) r, mode_cnt.p, mode_first.p, s);
       if (out->z) CK(cudaMemcpyAsync(out->z + r * n, snap_z.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
       if (out->weights) CK(cudaMemcpyAsync(out->weights + r * n, snap_w.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
       if (out->Y) CK(cudaMemcpyAsync(out->Y + r * (size_t) n * d, snap_Y.p, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
@@ -326,6 +331,10 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
   if (out->mu) CK(cudaMemcpyAsync(out->mu, snap_mu.p, sizeof(double) * nsnap * q * d, cudaMemcpyDeviceToHost, s));
   if (out->lambda) CK(cudaMemcpyAsync(out->lambda, snap_lambda.p, sizeof(double) * nsnap * d * d, cudaMemcpyDeviceToHost, s));
   if (out->Y_mean) CK(cudaMemcpyAsync(out->Y_mean, Ymean.p, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+  if (out->z_mode) {
+    launch_mode_final(mode_cnt.p, mode_first.p, n, q, snap_z.p, s);
+    CK(cudaMemcpyAsync(out->z_mode, snap_z.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaStreamSynchronize(s));
   if (out->mu)
     for (int k = 0; k < q; k++)

@@ -51,6 +51,36 @@ __global__ void k_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, in
   for (int c = 0; c < d; c++) out[(size_t) c * dst_ld + o] = Yp[(size_t) c * src_ld + i] + ybar[c];
 }
 
+// Per-spot label histogram over the kept snapshots, for the mode the R callers compute with apply(zs, 2, Mode)
+// (R/spatialCluster.R:204-213, R/spatialEnhance.R:450-458).  z1: one snapshot, 1-based labels in the caller's
+// order.  cnt / first: q x n; `first` keeps the row in which a label first appeared (Mode()'s tie rule).
+__global__ void k_mode_accumulate(const int32_t *z1, int64_t n, int q, uint32_t row, uint32_t *cnt, uint32_t *first) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = z1[i] - 1;
+  if ((unsigned) k >= (unsigned) q) return;
+  const size_t e = (size_t) k * n + i;
+  const uint32_t c = cnt[e];
+  if (c == 0u) first[e] = row;
+  cnt[e] = c + 1u;
+}
+
+// R/utils.R:63-66  Mode(x) = ux[which.max(tabulate(match(x, ux)))], ux = unique(x): the most frequent label,
+// ties broken by the earliest first appearance.  0 where no snapshot was kept.
+__global__ void k_mode_final(const uint32_t *cnt, const uint32_t *first, int64_t n, int q, int32_t *out) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int best = -1;
+  uint32_t bc = 0u, bf = 0u;
+  for (int k = 0; k < q; k++) {
+    const uint32_t c = cnt[(size_t) k * n + i];
+    if (c == 0u) continue;
+    const uint32_t f = first[(size_t) k * n + i];
+    if (c > bc || (c == bc && f < bf)) { best = k; bc = c; bf = f; }
+  }
+  out[i] = best + 1;
+}
+
 // running mean of Y snapshots: mean += (Y - mean) / count   (R/spatialEnhance.R:441)
 __global__ void k_running_mean(const double *snap, double *mean, int64_t len, double inv_count) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,6 +227,17 @@ void launch_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int
 void launch_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, const int32_t *orig,
                        const double *ybar, double *out, int64_t dst_ld, cudaStream_t s) {
   k_snapshot_Y<<<(unsigned) ((count + 255) / 256), 256, 0, s>>>(Yp, src_ld, count, d, orig, ybar, out, dst_ld);
+  g_launches++;
+}
+void launch_mode_accumulate(const int32_t *z1, int64_t n, int q, uint32_t row, uint32_t *cnt, uint32_t *first,
+                            cudaStream_t s) {
+  if (n <= 0) return;
+  k_mode_accumulate<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(z1, n, q, row, cnt, first);
+  g_launches++;
+}
+void launch_mode_final(const uint32_t *cnt, const uint32_t *first, int64_t n, int q, int32_t *out, cudaStream_t s) {
+  if (n <= 0) return;
+  k_mode_final<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(cnt, first, n, q, out);
   g_launches++;
 }
 void launch_running_mean(const double *snap, double *mean, int64_t len, double inv_count, cudaStream_t s) {

@@ -19,6 +19,9 @@ void launch_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int
                      double *w_out, cudaStream_t s, int64_t orig_off = 0);
 void launch_snapshot_Y(const double *Yp, int64_t src_ld, int64_t count, int d, const int32_t *orig,
                        const double *ybar, double *out, int64_t dst_ld, cudaStream_t s);
+void launch_mode_accumulate(const int32_t *z1, int64_t n, int q, uint32_t row, uint32_t *cnt, uint32_t *first,
+                            cudaStream_t s);
+void launch_mode_final(const uint32_t *cnt, const uint32_t *first, int64_t n, int q, int32_t *out, cudaStream_t s);
 void launch_running_mean(const double *snap, double *mean, int64_t len, double inv_count, cudaStream_t s);
 void launch_reduce_groups(const double *partials, const int32_t *group_start, int ngroups, int E,
                           double *gsum, cudaStream_t s, const uint32_t *gepoch = nullptr, size_t par_stride = 0);

@@ -65,24 +65,34 @@ def _cluster_args(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha
 
 
 def _run_cluster(model, precision, Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta,
-                 seed=0, compat=COMPAT_REFERENCE, device=0, colour=None, groups=0, world=1, rank=0, comm_id=None):
+                 seed=0, compat=COMPAT_REFERENCE, device=0, colour=None, groups=0, world=1, rank=0, comm_id=None,
+                 mode_from=None, keep_z=True, keep_weights=True):
+    """mode_from: also return 'z_mode', the per-spot mode of the label snapshots r >= mode_from with R's Mode() tie
+    rule, computed on the device (what spatialCluster does with apply(zs, 2, Mode), R/spatialCluster.R:204-213);
+    keep_z / keep_weights = False: the snapshot matrices are not materialised (they never leave the GPU)."""
     keep = _Keep()
     a = _cluster_args(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, model, precision,
                       seed, compat, device, colour, keep, groups, world, rank, comm_id)
     nsnap = nrep // thin + 1
     nl = q if precision == "variable" else 1
-    z = np.zeros((nsnap, n), dtype=np.int32)
+    z = np.zeros((nsnap, n), dtype=np.int32) if keep_z else None
     mu = np.zeros((nsnap, q * d))
     lam = np.zeros((nsnap, nl, d * d))
-    w = np.zeros((nsnap, n)) if model == "t" else None
+    w = np.zeros((nsnap, n)) if model == "t" and keep_weights else None
     pl = np.zeros(nrep)
+    zm = np.zeros(n, dtype=np.int32) if mode_from is not None else None
     o = ClusterOut()
     o.z, o.mu, o.lambda_, o.weights, o.plogLik = ptr(z), ptr(mu), ptr(lam), ptr(w), ptr(pl)
+    o.z_mode, o.mode_from = ptr(zm), 0 if mode_from is None else int(mode_from)
     check(lib().bsb200_cluster(C.byref(a), C.byref(o)))
     lam_m = lam.reshape(nsnap, nl, d, d).transpose(0, 1, 3, 2)   # col-major -> [i, j]
-    out = {"z": z, "mu": mu, "lambda": lam_m if nl > 1 else lam_m[:, 0], "plogLik": pl}
-    if model == "t":
+    out = {"mu": mu, "lambda": lam_m if nl > 1 else lam_m[:, 0], "plogLik": pl}
+    if z is not None:
+        out["z"] = z
+    if w is not None:
         out["weights"] = w
+    if zm is not None:
+        out["z_mode"] = zm
     out["_info"] = {"ncolours": o.ncolours, "setup_ms": o.setup_ms, "device_ms": o.device_ms, "rows_done": o.rows_done,
                     "own": (int(o.own_lo), int(o.own_hi))}
     return out
@@ -168,10 +178,11 @@ def cluster(Y, q, df_j, init=None, model="t", precision="equal", mu0=None, lambd
 
 def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin, n, n0, d, gamma, q, init,
                    subspots, verbose, jitter_scale, adapt_before, c, mu0, lambda0, alpha, beta, thread_num=1,
-                   seed=0, device=0, keep_Y=True, mean_from=None):
+                   seed=0, device=0, keep_Y=True, mean_from=None, mode_from=None):
     """iterate_deconv (src/cluster.cpp:742-1141).  spot_neighbors: "a,b,c" strings / None (NA), or a
     CSR tuple.  Y (n x d) is not mutated (quirk Q10).  mean_from: also return the running mean of the
-    Y snapshots r >= mean_from as 'Y_mean' (what spatialEnhance computes, R/spatialEnhance.R:441)."""
+    Y snapshots r >= mean_from as 'Y_mean' (what spatialEnhance computes, R/spatialEnhance.R:441); mode_from: also
+    return 'z_mode', the per-subspot mode of the label snapshots r >= mode_from (R/spatialEnhance.R:450-458)."""
     keep = _Keep()
     sp, si = spot_neighbors if isinstance(spot_neighbors, tuple) else neighbors.convert_neighbors(spot_neighbors)
     Y = np.asarray(Y, dtype=np.float64)
@@ -203,6 +214,8 @@ def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin
     o = DeconvOut()
     o.z, o.mu, o.lambda_, o.weights, o.Y, o.Y_mean = ptr(z), ptr(mu), ptr(lam), ptr(w), ptr(Yo), ptr(Ym)
     o.mean_from = 0 if mean_from is None else int(mean_from)
+    zm = np.zeros(n, dtype=np.int32) if mode_from is not None else None
+    o.z_mode, o.mode_from = ptr(zm), 0 if mode_from is None else int(mode_from)
     o.Ychange, o.plogLik, o.df_j = ptr(ych), ptr(pl), ptr(dfj)
     check(lib().bsb200_deconv(C.byref(a), C.byref(o)))
     out = {"z": z, "mu": mu, "lambda": lam.reshape(nsnap, d, d).transpose(0, 2, 1), "weights": w, "Ychange": ych,
@@ -212,6 +225,8 @@ def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin
         out["Y"] = Yo.transpose(0, 2, 1)   # nsnap x n x d
     if mean_from is not None:
         out["Y_mean"] = Ym.T.copy()
+    if zm is not None:
+        out["z_mode"] = zm
     return out
 
 

@@ -145,6 +145,13 @@ typedef struct bsb200_cluster_out {
   double device_ms;  /* out: device time of the sampling loop (CUDA events)             */
   int64_t own_lo, own_hi; /* out: spots [own_lo, own_hi) of z / weights were written by this rank
                              (all of them when world <= 1); mu / lambda / plogLik are complete on every rank */
+  /* Optional device-side post-sampling reduction: the per-spot MODE of the label snapshots of rows
+   * r >= mode_from, with R's Mode() tie rule (R/utils.R:63-66: among equally frequent labels the one that appears
+   * first in the kept rows) -- what spatialCluster() computes with apply(zs, 2, Mode) (R/spatialCluster.R:204-213,
+   * mode_from = burn.in %/% thin + 1).  n int32, 1-based; 0 where no row was kept.  With z == NULL the label
+   * snapshots never leave the GPU (440 MB per 11 rows at 10M spots). */
+  int32_t *z_mode;
+  int32_t mode_from;
 } bsb200_cluster_out;
 
 int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out);
@@ -259,6 +266,9 @@ typedef struct bsb200_deconv_out {
   double *Y;        /* nsnap x (n x d col-major), or NULL                 */
   double *Y_mean;   /* optional running mean of the Y snapshots r >= mean_from (n x d col-major) */
   int32_t mean_from;
+  int32_t mode_from; /* rows r >= mode_from enter z_mode (below)                                  */
+  int32_t *z_mode;   /* optional per-subspot mode of the label snapshots, R's Mode() tie rule
+                        (R/spatialEnhance.R:450-458, R/utils.R:63-66); n int32, 1-based            */
   double *Ychange;  /* nrep, [0] = NaN                                    */
   double *plogLik;  /* nrep, [0] = NaN                                    */
   int64_t *df_j;    /* n x 4 col-major, 1-based zero padded               */

@@ -343,3 +343,20 @@ def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin
     if keep_Y:
         out["Y"] = Yo.transpose(0, 2, 1)   # nsnap x n x d
     return out
+
+
+def mode_rows(zs):
+    """R's Mode applied to every column of the kept label rows: apply(zs, 2, Mode) with
+    Mode(x) = ux[which.max(tabulate(match(x, ux)))], ux = unique(x)   (R/utils.R:63-66, R/spatialCluster.R:204-213):
+    the most frequent label; among equally frequent ones the label that appears FIRST in the column."""
+    zs = np.asarray(zs)
+    out = np.zeros(zs.shape[1], dtype=np.int32)
+    for j in range(zs.shape[1]):
+        x = zs[:, j]
+        ux = []
+        for v in x:                      # unique(): order of first appearance
+            if v not in ux:
+                ux.append(v)
+        counts = [int(np.sum(x == v)) for v in ux]    # tabulate(match(x, ux))
+        out[j] = ux[int(np.argmax(counts))]           # which.max: first maximum
+    return out

@@ -220,3 +220,23 @@ def test_golden_vectors(oracle):
         assert np.array_equal(out["z"], gold[case["key"] + "_z"])
         assert np.allclose(out["mu"], gold[case["key"] + "_mu"], rtol=1e-12, atol=1e-12)
         assert np.allclose(out["plogLik"][1:], gold[case["key"] + "_plogLik"][1:], rtol=1e-12)
+
+
+def test_mode_rows_is_R_Mode():
+    """R/utils.R:63-66: most frequent value, ties to the earliest first appearance."""
+    from oracle import oracle as O
+    zs = np.array([[2, 1, 3, 1],
+                   [1, 1, 3, 2],
+                   [2, 3, 1, 2],
+                   [1, 3, 1, 3]])
+    # col 0: 2,1,2,1 -> tie, 2 appears first; col 1: 1,1,3,3 -> 1; col 2: 3,3,1,1 -> 3; col 3: 1,2,2,3 -> 2
+    assert O.mode_rows(zs).tolist() == [2, 1, 3, 2]
+    assert O.mode_rows(zs[:1]).tolist() == [2, 1, 3, 1]
+    rng = np.random.default_rng(0)
+    big = rng.integers(1, 5, size=(9, 200))
+    got = O.mode_rows(big)
+    for j in range(200):
+        c = np.bincount(big[:, j], minlength=5)
+        assert c[got[j]] == c.max()
+        first = {v: int(np.argmax(big[:, j] == v)) for v in range(1, 5) if c[v] == c.max()}
+        assert got[j] == min(first, key=first.get)
