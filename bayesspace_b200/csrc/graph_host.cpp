@@ -333,7 +333,12 @@ int bsb200_neighbors_lattice(const int32_t *array_row, const int32_t *array_col,
           const int32_t u = grid[(size_t) (r * W + c)];
           if (u >= 0) nb[cnt++] = u;
         }
-        std::sort(nb, nb + cnt);
+        for (int a = 1; a < cnt; a++) {   // at most 6 entries: insertion sort (ascending ids, R/spatialCluster.R:263-267)
+          const int32_t v = nb[a];
+          int b = a - 1;
+          for (; b >= 0 && nb[b] > v; b--) nb[b + 1] = nb[b];
+          nb[b + 1] = v;
+        }
         if (ptr) ptr[j] = total;
         if (fill && total + cnt <= cap)
           for (int e = 0; e < cnt; e++) idx[total + e] = nb[e];

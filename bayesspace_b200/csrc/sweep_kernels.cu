@@ -66,7 +66,7 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(int D, int q, int nl, int
 template <int D, bool TDIST, bool VVV>
 __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP, NTILES = TileGeom<D>::NTILES, NT = TileGeom<D>::NT;
+  constexpr int NP = D * (D + 1) / 2, DP = TileGeom<D>::DP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = a.PL.q, nl = a.PL.nl, E = a.SL.E;
   const SweepSmem L = sweep_smem_layout(D, q, nl, NP, E, TDIST, VVV, a.SL.nlT > 1, a.maxdeg);
