@@ -201,3 +201,46 @@ def test_argument_checks_precede_the_device(bsb):
         bsb.iterate(Ybig, csr, 10, 1, w.n, 40, w.gamma, w.q, w.init, np.zeros(40), np.eye(40), w.alpha, w.beta)
     assert ei.value.code == -7
     assert bsb.cluster(w.Y, 1, csr)["z"].shape == (1, w.n)      # q == 1 shortcut (R/spatialCluster.R:89-91)
+
+
+def test_header_is_plain_c_and_a_c_program_can_bind_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: include/bsb200.h must compile as C99 (no C++/torch types), the ctypes mirror
+    must agree with the header on the struct sizes, and a C program linked against libbsb200.so must be able to call it."""
+    import ctypes
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "bsb200.h"
+int main(void) {
+  bsb200_cluster_args a; bsb200_cluster_out o; bsb200_deconv_args da; bsb200_deconv_out dout;
+  memset(&a, 0, sizeof a); memset(&o, 0, sizeof o); memset(&da, 0, sizeof da); memset(&dout, 0, sizeof dout);
+  printf("%zu %zu %zu %zu\n", sizeof a, sizeof o, sizeof da, sizeof dout);
+  printf("%d\n", bsb200_version());
+  /* host-only entry point: neighbours of a 2 x 2 square lattice */
+  int32_t row[4] = {1, 1, 2, 2}, col[4] = {1, 2, 1, 2}, idx[16];
+  int64_t ptr[5], nnz = 0;
+  int rc = bsb200_neighbors_lattice(row, col, 4, BSB200_PLATFORM_SQUARE, ptr, idx, 16, &nnz);
+  printf("%d %lld\n", rc, (long long) nnz);
+  /* invalid arguments are rejected before any device work, with a message */
+  rc = bsb200_cluster(&a, &o);
+  printf("%d %s\n", rc, bsb200_last_error());
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "bayesspace_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lbsb200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    sizes = [int(v) for v in out[0].split()]
+    from bayesspace_b200 import _lib
+    assert sizes == [ctypes.sizeof(_lib.ClusterArgs), ctypes.sizeof(_lib.ClusterOut), ctypes.sizeof(_lib.DeconvArgs),
+                     ctypes.sizeof(_lib.DeconvOut)]
+    assert int(out[1]) > 0
+    assert out[2] == "0 8"                     # 4 spots x 2 neighbours each
+    rc, msg = out[3].split(" ", 1)
+    assert int(rc) == _lib.ERR_INVALID and len(msg) > 0
