@@ -68,7 +68,7 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(g) for g in self.gpus]
+            self.handles = [self._nvml_handle(pynvml, g) for g in self.gpus]
             self.mode = "nvml"
             self.t = threading.Thread(target=self._poll_nvml, daemon=True)
             self.t.start()
@@ -85,6 +85,20 @@ class ClockSampler:
         if self.mode:
             self.first.wait(timeout=10.0)
         return self
+
+    @staticmethod
+    def _nvml_handle(nv, cuda_index):
+        """NVML enumerates every GPU of the box; CUDA ordinals follow CUDA_VISIBLE_DEVICES when it is set."""
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if cuda_index < len(vis):
+            v = vis[cuda_index]
+            if v.isdigit():
+                return nv.nvmlDeviceGetHandleByIndex(int(v))
+            try:
+                return nv.nvmlDeviceGetHandleByUUID(v if isinstance(v, bytes) else v.encode())
+            except Exception:
+                return nv.nvmlDeviceGetHandleByUUID(v)
+        return nv.nvmlDeviceGetHandleByIndex(cuda_index)
 
     def _poll_nvml(self):
         nv = self.nv
