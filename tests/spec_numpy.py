@@ -1,0 +1,143 @@
+"""A second, independent restatement of the four cluster samplers, written in numpy directly from the reference's
+lines (/root/reference/src/cluster.cpp) with numpy.linalg doing what Armadillo does there -- `inv`, `chol` per spot,
+exactly the reference's cost profile, none of the algebraic shortcuts of the CUDA path and none of oracle/ref_cpu.cpp's
+code.  Test infrastructure: tests/test_oracle.py runs it beside the C++ oracle on the same keyed variates; the two
+must produce the same chain.  (The variates themselves come from the oracle's Philox primitives, which are pinned
+separately by Random123 known answers and distribution tests.)
+
+    iterate        src/cluster.cpp:217-321      iterate_vvv    :323-444
+    iterate_t      :446-568                     iterate_t_vvv  :570-710
+    dmvnrm_arma_fast :83-106, inplace_tri_mat_mult_t :68-78
+    rmvnorm / rwish (RcppDist), sample (Rcpp sugar): SURVEY.md App. C
+"""
+import numpy as np
+
+P_MU, P_WISH_NORM, P_WISH_CHI, P_SPOT_U, P_SPOT_GAMMA = 1, 2, 3, 4, 5
+LOG2PI = np.log(2.0 * np.pi)
+
+
+def chol_upper(S):
+    """arma::chol: upper R with R^T R = S."""
+    return np.linalg.cholesky(S).T
+
+
+def dmvnrm_arma_fast(x, mean, sigma):
+    """:83-106 with logd = true, for one row x.  rooti = inv(trimatu(chol(sigma))); z = rooti * (x - mean) through
+    inplace_tri_mat_mult_t (row i of the UPPER triangle times z[i:]) -- the reference's form (quirk Q1)."""
+    d = x.shape[0]
+    rooti = np.linalg.inv(np.triu(chol_upper(sigma)))
+    z = x - mean
+    for i in range(d):                       # :71-76, in place: entries j >= i are still the old ones
+        z[i] = np.dot(rooti[i, i:], z[i:])
+    return np.sum(np.log(np.diag(rooti))) - 0.5 * d * LOG2PI - 0.5 * np.dot(z, z)
+
+
+def rmvnorm1(O, seed, index, it, mean, var):
+    """RcppDist rmvnorm(1, mean, var) = z chol(var) + mean, z ~ N(0, I) row."""
+    z = O.normal(seed, P_MU, index, it, 0, mean.shape[0])
+    return z @ chol_upper(var) + mean
+
+
+def rwish(O, seed, index, it, df, S):
+    """RcppDist rwish(int df, S): Bartlett factor A (lower; N(0,1) below the diagonal, sqrt(chisq(df - i)) on it),
+    result (A^T chol(S))^T (A^T chol(S))."""
+    d = S.shape[0]
+    df = int(df)                              # the C++ parameter is an int (quirk Q4)
+    A = np.zeros((d, d))
+    for i in range(1, d):
+        A[i, :i] = O.normal(seed, P_WISH_NORM, index, it, i * (i - 1) // 2, i)
+    for i in range(d):
+        A[i, i] = np.sqrt(O.gamma(seed, P_WISH_CHI, index * 1024 + i, 1, it, (df - i) / 2.0, 2.0)[0])
+    B = A.T @ chol_upper(S)
+    return B.T @ B
+
+
+def sample_without(q, z_prev, u):
+    """sample(qvec[qvec != z_prev], 1): element floor(len * u) of the remaining labels, ascending."""
+    rest = [k for k in range(1, q + 1) if k != z_prev]
+    return rest[min(int(np.floor(len(rest) * u)), len(rest) - 1)]
+
+
+def sample_two(z_prev, z_new, p, u):
+    """sample({z_prev, z_new}, 1, TRUE, {1 - p, p}): Rcpp sugar sorts the probabilities in DECREASING order and
+    inverts the cumulative sum with one uniform."""
+    items = [(1.0 - p, z_prev), (p, z_new)]
+    if p >= 0.5:                              # stable descending order: z_new first when p >= 1 - p ... ties: p == .5
+        items = [(p, z_new), (1.0 - p, z_prev)]
+    return items[0][1] if u <= items[0][0] else items[1][1]
+
+
+def run(O, variant, Y, nbrs, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, seed):
+    """variant: 'iterate' | 'iterate_vvv' | 'iterate_t' | 'iterate_t_vvv'.  nbrs: list of 0-based neighbour arrays."""
+    tdist, vvv = variant in ("iterate_t", "iterate_t_vvv"), variant.endswith("vvv")
+    nsnap = nrep // thin + 1
+    zs = np.zeros((nsnap, n), dtype=np.int64)
+    mus = np.zeros((nsnap, q * d))
+    lams = [None] * nsnap
+    ws = np.zeros((nsnap, n))
+    plogLik = np.full(nrep, np.nan)
+    z = np.array(init, dtype=np.int64)
+    w = np.ones(n)
+    lam = [lambda0.copy() for _ in range(q)] if vvv else [lambda0.copy()]
+    sig = [np.linalg.inv(lambda0) for _ in lam]
+    zs[0], mus[0], ws[0] = z, np.tile(mu0, q), w
+    lams[0] = [m.copy() for m in lam] if vvv else lam[0].copy()
+    V = beta * np.eye(d)
+    for i in range(1, nrep):
+        # ---- mu (:247-258, :482-492)
+        mu = np.zeros((q, d))
+        for k in range(1, q + 1):
+            idx = np.where(z == k)[0]
+            wk = w[idx] if tdist else np.ones(len(idx))
+            n_i = wk.sum() if tdist else len(idx)
+            ysum = (Y[idx] * wk[:, None]).sum(axis=0)
+            L = lam[k - 1] if vvv else lam[0]
+            var = np.linalg.inv(lambda0 + n_i * L)
+            mean = var @ (lambda0 @ mu0 + L @ ysum)
+            mu[k - 1] = rmvnorm1(O, seed, k - 1, i, mean, var)
+        # ---- lambda (:260-270, :382-390, :500-505, :635-644)
+        mu_long = mu[z - 1]
+        R = Y - mu_long
+        if vvv:
+            for k in range(1, q + 1):
+                idx = np.where(z == k)[0]
+                wk = w[idx] if tdist else np.ones(len(idx))
+                S = (R[idx] * wk[:, None]).T @ R[idx]
+                lam[k - 1] = rwish(O, seed, k - 1, i, len(idx) + alpha, np.linalg.inv(V + S))
+                sig[k - 1] = np.linalg.inv(lam[k - 1])
+        else:
+            S = (R * (w if tdist else np.ones(n))[:, None]).T @ R
+            lam[0] = rwish(O, seed, 0, i, n + alpha, np.linalg.inv(V + S))
+            sig[0] = np.linalg.inv(lam[0])
+        # ---- z (and w) scan (:272-306, :392-430, :507-553, :646-695)
+        w_alpha = float((d + 4) // 2)             # integer division in the reference (quirk Q2)
+        plj = np.zeros(n)
+        for j in range(n):
+            z_prev = int(z[j])
+            kp = z_prev - 1 if vvv else 0
+            if tdist:
+                r = Y[j] - mu_long[j]
+                w_beta = 2.0 / (r @ lam[kp] @ r + 4.0)
+                w[j] = O.gamma(seed, P_SPOT_GAMMA, j, 1, i, w_alpha, w_beta)[0]
+            u_prop, u_acc = O.uniform2(seed, P_SPOT_U, j, i, 0)
+            z_new = sample_without(q, z_prev, u_prop)
+            kn = z_new - 1 if vvv else 0
+            scale = w[j] if tdist else 1.0
+            h_prev = dmvnrm_arma_fast(Y[j].copy(), mu[z_prev - 1], sig[kp] / scale)
+            h_new = dmvnrm_arma_fast(Y[j].copy(), mu[z_new - 1], sig[kn] / scale)
+            nb = np.asarray(nbrs[j], dtype=np.int64)
+            if nb.size:
+                if variant == "iterate_vvv":      # :404 compares the neighbour INDICES with the label (quirk Q3)
+                    h_prev += gamma / nb.size * 2 * np.sum(nb == z_prev)
+                else:
+                    h_prev += gamma / nb.size * 2 * np.sum(z[nb] == z_prev)
+                h_new += gamma / nb.size * 2 * np.sum(z[nb] == z_new)
+            p = min(np.exp(h_new - h_prev), 1.0)
+            z[j] = sample_two(z_prev, z_new, p, u_acc)
+            plj[j] = h_prev
+        plogLik[i] = plj.sum()
+        if (i + 1) % thin == 0:
+            r_ = (i + 1) // thin
+            zs[r_], mus[r_], ws[r_] = z, mu.reshape(-1), w
+            lams[r_] = [m.copy() for m in lam] if vvv else lam[0].copy()
+    return {"z": zs, "mu": mus, "lambda": lams, "weights": ws, "plogLik": plogLik}

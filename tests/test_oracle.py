@@ -240,3 +240,32 @@ def test_mode_rows_is_R_Mode():
         assert c[got[j]] == c.max()
         first = {v: int(np.argmax(big[:, j] == v)) for v in range(1, 5) if c[v] == c.max()}
         assert got[j] == min(first, key=first.get)
+
+
+@pytest.mark.parametrize("variant", ["iterate", "iterate_vvv", "iterate_t", "iterate_t_vvv"])
+@pytest.mark.parametrize("name", ["tiny_hex", "small_sq"])
+def test_oracle_agrees_with_an_independent_numpy_restatement(oracle, variant, name):
+    """Two restatements of the reference written independently from its lines -- oracle/ref_cpu.cpp (C++) and
+    tests/spec_numpy.py (numpy.linalg, the reference's own operation order) -- fed the same keyed variates must
+    produce the same chain in the reference's sequential scan: labels identical, parameters to rounding."""
+    import spec_numpy
+    from bayesspace_b200 import synth
+    w = synth.make_workload(name)
+    ptr, idx = oracle.lattice_neighbors(w.array_row, w.array_col, w.platform)
+    nbrs = [idx[ptr[j]:ptr[j + 1]] for j in range(w.n)]
+    nrep, thin, seed = 7, 2, 31
+    Y = np.ascontiguousarray(w.Y)
+    ref = getattr(oracle, variant)(w.Y, (ptr, idx), nrep, thin, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0,
+                                   w.alpha, w.beta, seed=seed)
+    got = spec_numpy.run(oracle, variant, Y, nbrs, nrep, thin, w.n, w.d, w.gamma, w.q, w.init, np.asarray(w.mu0),
+                         np.asarray(w.lambda0), w.alpha, w.beta, seed)
+    assert np.array_equal(got["z"], ref["z"])
+    assert np.allclose(got["mu"], ref["mu"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(got["plogLik"][1:], ref["plogLik"][1:], rtol=1e-11, atol=0)
+    if variant.startswith("iterate_t"):
+        assert np.allclose(got["weights"], ref["weights"], rtol=1e-10, atol=0)
+    for r in range(nrep // thin + 1):
+        lam_ref = np.asarray(ref["lambda"][r])
+        lam_got = np.asarray(got["lambda"][r])
+        assert lam_got.shape == lam_ref.shape
+        assert np.allclose(lam_got, lam_ref, rtol=1e-8, atol=1e-12)
