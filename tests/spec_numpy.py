@@ -141,3 +141,120 @@ def run(O, variant, Y, nbrs, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alp
             zs[r_], mus[r_], ws[r_] = z, mu.reshape(-1), w
             lams[r_] = [m.copy() for m in lam] if vvv else lam[0].copy()
     return {"z": zs, "mu": mus, "lambda": lams, "weights": ws, "plogLik": plogLik}
+
+
+# ---- iterate_deconv (src/cluster.cpp:742-1141), adaptive_mcmc (:49-65), dmvnrm_prec_arma_fast (:109-132) -----
+P_ERR, P_SPOT_YACC = 6, 7
+
+
+def dmvnrm_prec_arma_fast(x, mean, lam):
+    """:109-132 with logd = true, one row: rooti = trimatu(chol(lambda)); z = rooti (x - mean)."""
+    d = x.shape[0]
+    rooti = np.triu(chol_upper(lam))
+    z = x - mean
+    for i in range(d):
+        z[i] = np.dot(rooti[i, i:], z[i:])
+    return np.sum(np.log(np.diag(rooti))) - 0.5 * d * LOG2PI - 0.5 * np.dot(z, z)
+
+
+def adaptive_mcmc(acc, target, it, A, u):
+    """:49-65  chol(A (I + eta (acc - target) u^T u / |u|^2) A^T, "lower"), eta = min(1, d it^(-2/3))."""
+    d = u.shape[0]
+    eta = min(1.0, d * float(it) ** (-2.0 / 3.0))
+    M = A @ (np.eye(d) + eta * (acc - target) * np.outer(u, u) / np.dot(u, u)) @ A.T
+    return np.linalg.cholesky(M)
+
+
+def run_deconv(O, Y, sub_nbrs, tdist, nrep, thin, n, n0, d, gamma, q, init, S, jitter_scale, adapt_before, c,
+               mu0, lambda0, alpha, beta, seed):
+    """Subspot s = r * n0 + j0.  sub_nbrs: 0-based neighbour arrays of the subspots."""
+    Y = np.array(Y, dtype=np.float64)          # the reference mutates the caller's matrix; here a private copy
+    Y0 = Y[:n0].copy()                          # :777
+    nsnap = nrep // thin + 1
+    zs = np.zeros((nsnap, n), dtype=np.int64)
+    mus = np.zeros((nsnap, q * d))
+    lams, Ys = [None] * nsnap, [None] * nsnap
+    ws = np.zeros((nsnap, n))
+    Ychange, plogLik = np.full(nrep, np.nan), np.full(nrep, np.nan)
+    z = np.array(init, dtype=np.int64)
+    w = np.ones(n)
+    lam = lambda0.copy()
+    zs[0], mus[0], ws[0], lams[0], Ys[0] = z, np.tile(mu0, q), w, lam.copy(), Y.copy()
+    V = beta * np.eye(d)
+    w_alpha = float((d + 4) // 2)               # :809, integer division
+    jitter_scale = jitter_scale / d             # :814
+    adaptive = jitter_scale == 0.0
+    A = [np.eye(d) for _ in range(n)] if adaptive else None
+    acc_n, rej_n = np.zeros(n0, dtype=np.int64), np.zeros(n0, dtype=np.int64)
+    rows = np.arange(S) * n0
+    for i in range(1, nrep):
+        # ---- mu, lambda, jitter draws (:880-908)
+        mu = np.zeros((q, d))
+        for k in range(1, q + 1):
+            idx = np.where(z == k)[0]
+            ysum = (Y[idx] * w[idx][:, None]).sum(axis=0)
+            var = np.linalg.inv(lambda0 + w[idx].sum() * lam)
+            mean = var @ (lambda0 @ mu0 + lam @ ysum)
+            mu[k - 1] = rmvnorm1(O, seed, k - 1, i, mean, var)
+        mu_long = mu[z - 1]
+        R = Y - mu_long
+        lam = rwish(O, seed, 0, i, n + alpha, np.linalg.inv(V + (R * w[:, None]).T @ R))
+        sd = 1.0 if adaptive else np.sqrt(jitter_scale)
+        error = np.stack([O.normal(seed, P_ERR, s, i, 0, d) for s in range(n)]) * sd
+        # ---- proposals and their joint acceptance probability per parent spot (:913-962)
+        Y_new = np.zeros_like(Y)
+        accp = np.zeros(n0)
+        for j0 in range(n0):
+            ss = rows + j0
+            e = error[ss].copy()
+            if adaptive:
+                for r in range(S):
+                    e[r] = A[ss[r]] @ e[r]
+            e -= e.sum(axis=0) / S                  # zero-sum jitter: the parent's mean is preserved
+            Yp, Yn = Y[ss], Y[ss] + e
+            p_prev = p_new = 0.0
+            for r in range(S):
+                L = lam * w[ss[r]]
+                p_prev += dmvnrm_prec_arma_fast(Yp[r].copy(), mu_long[ss[r]], L) - c * np.sum((Yp[r] - Y0[j0]) ** 2)
+                p_new += dmvnrm_prec_arma_fast(Yn[r].copy(), mu_long[ss[r]], L) - c * np.sum((Yn[r] - Y0[j0]) ** 2)
+            accp[j0] = min(np.exp(p_new - p_prev), 1.0)
+            Y_new[ss] = Yn
+        # ---- accept / reject, RAM update, w, z (:969-1053)
+        updates, ll = 0, np.zeros(n)
+        for j0 in range(n0):
+            ss = rows + j0
+            u_y = O.uniform2(seed, P_SPOT_YACC, j0, i, 0)[0]
+            if sample_two(0, 1, accp[j0], u_y) == 1:
+                Y[ss] = Y_new[ss]
+                acc_n[j0] += 1
+                updates += 1
+            else:
+                rej_n[j0] += 1
+            for r in range(S):
+                s = ss[r]
+                if adaptive and i > 10 and (adapt_before == 0 or i <= adapt_before):
+                    A[s] = adaptive_mcmc(acc_n[j0] / float(acc_n[j0] + rej_n[j0]), 0.234, i, A[s], error[s])
+                if tdist:
+                    rr = Y[s] - mu_long[s]
+                    w[s] = O.gamma(seed, P_SPOT_GAMMA, s, 1, i, w_alpha, 2.0 / (rr @ lam @ rr + 4.0))[0]
+                z_prev = int(z[s])
+                u_prop, u_acc = O.uniform2(seed, P_SPOT_U, s, i, 0)
+                z_new = sample_without(q, z_prev, u_prop)
+                l_prev = dmvnrm_prec_arma_fast(Y[s].copy(), mu[z_prev - 1], lam * w[s])
+                l_new = dmvnrm_prec_arma_fast(Y[s].copy(), mu[z_new - 1], lam * w[s])
+                h_prev, h_new = l_prev, l_new
+                nb = np.asarray(sub_nbrs[s], dtype=np.int64)
+                if nb.size:
+                    h_prev += gamma / nb.size * 2 * np.sum(z[nb] == z_prev)
+                    h_new += gamma / nb.size * 2 * np.sum(z[nb] == z_new)
+                p = np.exp(h_new - h_prev)
+                yes = 1 if p >= 1 else sample_two(0, 1, p, u_acc)     # :1037-1046: no draw when p >= 1
+                if yes == 1:
+                    z[s] = z_new
+                ll[s] = l_new if yes == 1 else l_prev                 # likelihood only, of the resulting state
+        Ychange[i] = updates / float(n0)
+        plogLik[i] = ll.sum()
+        if (i + 1) % thin == 0:
+            r_ = (i + 1) // thin
+            zs[r_], mus[r_], ws[r_], lams[r_], Ys[r_] = z, mu.reshape(-1), w, lam.copy(), Y.copy()
+    return {"z": zs, "mu": mus, "lambda": lams, "weights": ws, "Y": Ys, "Ychange": Ychange, "plogLik": plogLik}

@@ -269,3 +269,35 @@ def test_oracle_agrees_with_an_independent_numpy_restatement(oracle, variant, na
         lam_got = np.asarray(got["lambda"][r])
         assert lam_got.shape == lam_ref.shape
         assert np.allclose(lam_got, lam_ref, rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("tdist,jitter_scale,adapt_before", [(True, 5.0, 0), (False, 5.0, 0), (True, 0.0, 0),
+                                                              (True, 0.0, 14)])
+def test_oracle_deconv_agrees_with_an_independent_numpy_restatement(oracle, tdist, jitter_scale, adapt_before):
+    """iterate_deconv (src/cluster.cpp:742-1141) restated twice, independently: same chain from the same variates,
+    for the fixed-jitter and the adaptive (RAM) proposal, normal and t errors."""
+    import spec_numpy
+    from bayesspace_b200 import synth
+    w = synth.make_workload("tiny_hex")
+    ptr, idx = oracle.lattice_neighbors(w.array_row, w.array_col, w.platform)
+    pos = np.c_[w.array_col.astype(float), w.array_row * np.sqrt(3.0)]
+    dc = synth.deconv_inputs(w.Y, pos, 1.0, np.sqrt(3.0), w.truth, platform="Visium")
+    strings = synth.neighbor_strings(ptr, idx)
+    nrep, thin, seed = 19, 3, 77
+    ref = oracle.iterate_deconv(dc["positions2"], dc["dist"], strings, dc["Y2"], tdist, nrep, thin, dc["n"], dc["n0"],
+                                w.d, 2.0, w.q, dc["init1"], dc["subspots"], False, jitter_scale, adapt_before, dc["c"],
+                                w.mu0, w.lambda0, w.alpha, w.beta, 1, seed=seed)
+    sp, si = oracle.find_subspot_neighbors((ptr, idx), dc["positions2"], dc["dist"])
+    sub_nbrs = [si[sp[s]:sp[s + 1]] for s in range(dc["n"])]
+    got = spec_numpy.run_deconv(oracle, dc["Y2"], sub_nbrs, tdist, nrep, thin, dc["n"], dc["n0"], w.d, 2.0, w.q,
+                                dc["init1"], dc["subspots"], jitter_scale, adapt_before, dc["c"], np.asarray(w.mu0),
+                                np.asarray(w.lambda0), w.alpha, w.beta, seed)
+    assert np.array_equal(got["z"], ref["z"])
+    assert np.array_equal(got["Ychange"][1:], ref["Ychange"][1:]) and np.isnan(ref["Ychange"][0])
+    assert np.nanmax(ref["Ychange"]) > 0, "no proposal accepted: the Y path would be untested"
+    assert np.allclose(got["mu"], ref["mu"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(got["plogLik"][1:], ref["plogLik"][1:], rtol=1e-11, atol=0)
+    assert np.allclose(got["weights"], ref["weights"], rtol=1e-10, atol=0)
+    for r in range(nrep // thin + 1):
+        assert np.allclose(np.asarray(got["lambda"][r]), np.asarray(ref["lambda"][r]), rtol=1e-8, atol=1e-12)
+        assert np.allclose(got["Y"][r], np.asarray(ref["Y"][r]), rtol=1e-10, atol=1e-11)
