@@ -8,7 +8,9 @@
 // this image, and its own tests pin no sampler numerics (only tests/testthat/test-find_neighbors.R
 // holds a known answer, reproduced in tests/).  The sampler arithmetic below is therefore
 // "parity unpinned": it follows src/cluster.cpp line by line, and App. C of SURVEY.md for the
-// un-vendored RcppDist / Rcpp-sugar / Armadillo semantics.
+// un-vendored RcppDist / Rcpp-sugar / Armadillo semantics.  Its reading of the reference is cross-checked by a
+// second, independent restatement (tests/spec_numpy.py, numpy.linalg in the reference's operation order): the two
+// must produce the same chains for all five samplers (tests/test_oracle.py).
 //
 // What is restated (file:line = /root/reference/...):
 //   dmvnrm_arma_fast            src/cluster.cpp:83-106   (incl. quirk Q1: T*x instead of x^T*T)
