@@ -258,3 +258,64 @@ def run_deconv(O, Y, sub_nbrs, tdist, nrep, thin, n, n0, d, gamma, q, init, S, j
             r_ = (i + 1) // thin
             zs[r_], mus[r_], ws[r_], lams[r_], Ys[r_] = z, mu.reshape(-1), w, lam.copy(), Y.copy()
     return {"z": zs, "mu": mus, "lambda": lams, "weights": ws, "Y": Ys, "Ychange": Ychange, "plogLik": plogLik}
+
+
+# ---- neighbour construction, restated from the R / C++ sources with pandas / numpy --------------------------
+def find_neighbors_lattice(array_row, array_col, platform):
+    """.find_neighbors (R/spatialCluster.R:227-302): cross-join the spots with the platform's offsets, left-merge the
+    candidate coordinates with the spot table, order by (primary, neighbour), split by primary, drop the NAs.
+    Returns the 0-based lists (df_j) and the 1-based comma strings / None (sce$spot.neighbors)."""
+    import pandas as pd
+    if platform == "Visium":
+        offsets = pd.DataFrame({"x.offset": [-2, 2, -1, 1, -1, 1], "y.offset": [0, 0, -1, -1, 1, 1]})
+    elif platform in ("VisiumHD", "ST"):
+        offsets = pd.DataFrame({"x.offset": [0, 1, 0, -1], "y.offset": [-1, 0, 1, 0]})
+    else:
+        raise ValueError('.find_neighbors: Unsupported platform "%s".' % platform)
+    n = len(array_row)
+    spots = pd.DataFrame({"spot.idx": np.arange(1, n + 1), "array_col": np.asarray(array_col, dtype=np.int64),
+                          "array_row": np.asarray(array_row, dtype=np.int64)})
+    cand = spots.merge(offsets, how="cross")
+    cand["x.pos"] = cand["array_col"] + cand["x.offset"]
+    cand["y.pos"] = cand["array_row"] + cand["y.offset"]
+    nb = cand.merge(spots, how="left", left_on=["x.pos", "y.pos"], right_on=["array_col", "array_row"],
+                    suffixes=(".primary", ".neighbor"))
+    nb = nb.sort_values(["spot.idx.primary", "spot.idx.neighbor"], kind="stable")
+    df_j, strings = [], []
+    groups = {k: v["spot.idx.neighbor"].dropna().astype(np.int64).to_numpy() for k, v in nb.groupby("spot.idx.primary")}
+    for j in range(1, n + 1):
+        x = groups.get(j, np.zeros(0, dtype=np.int64))
+        strings.append(None if len(x) == 0 else ",".join(str(int(v)) for v in x))
+        df_j.append(x - 1)
+    return df_j, strings
+
+
+def find_neighbors_radius(positions, radius, method="manhattan"):
+    """find_neighbors (R/utils.R:13-26): dense distance matrix, 0 < dist <= radius, which() order (ascending)."""
+    P = np.asarray(positions, dtype=np.float64)
+    diff = P[:, None, :] - P[None, :, :]
+    dist = np.abs(diff).sum(axis=2) if method == "manhattan" else np.sqrt((diff ** 2).sum(axis=2))
+    keep = (dist <= radius) & (dist > 0)
+    return [np.where(keep[i])[0] for i in range(P.shape[0])]
+
+
+def find_subspot_neighbors(spot_nbrs, positions, dist):
+    """src/cluster.cpp:161-215.  spot_nbrs: 0-based neighbour arrays of the n0 spots; subspot s = r * n0 + spot.
+    Candidates: for every candidate spot (the spot's neighbours in list order, then the spot itself) its S subspots
+    r = 0..S-1 (the column-major flattening of the S x (k+1) index matrix); kept where 1e-6 < Manhattan < dist."""
+    P = np.asarray(positions, dtype=np.float64)
+    n0 = len(spot_nbrs)
+    S = P.shape[0] // n0
+    if abs(P.shape[0] / n0 - S) > 1e-6:
+        raise RuntimeError("Invalid arguments!")
+    out = []
+    for s in range(P.shape[0]):
+        spot = s % n0
+        cand_spots = list(spot_nbrs[spot]) + [spot]
+        cand = np.array([r * n0 + c for c in cand_spots for r in range(S)], dtype=np.int64)
+        man = np.abs(P[cand] - P[s]).sum(axis=1)
+        keep = (man < dist) & (man > 1e-6)
+        if keep.sum() < 2:
+            raise RuntimeError("Error in finding neighbors of subspots!")
+        out.append(cand[keep])
+    return out

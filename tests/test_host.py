@@ -244,3 +244,74 @@ int main(void) {
     assert out[2] == "0 8"                     # 4 spots x 2 neighbours each
     rc, msg = out[3].split(" ", 1)
     assert int(rc) == _lib.ERR_INVALID and len(msg) > 0
+
+
+# ---- the product's graph builders against restatements written from the R / C++ sources ---------------------
+def _lists(ptr, idx):
+    return [np.asarray(idx[ptr[j]:ptr[j + 1]]) for j in range(len(ptr) - 1)]
+
+
+@pytest.mark.parametrize("platform", ["Visium", "ST"])
+def test_lattice_neighbors_match_the_R_restatement(bsb, oracle, platform):
+    """.find_neighbors restated with pandas merges exactly as R/spatialCluster.R:227-302 does it, on a lattice with
+    holes and a duplicated coordinate: product (host code of libbsb200.so), oracle and restatement must agree on the
+    lists, their order and the comma strings."""
+    import spec_numpy
+    from bayesspace_b200 import synth
+    rng = np.random.default_rng(4)
+    if platform == "Visium":
+        r, c = synth.hex_lattice(14, 11)
+    else:
+        r, c = synth.square_lattice(12, 13)
+    keep = rng.random(len(r)) > 0.15                      # holes in the tissue
+    r, c = r[keep], c[keep]
+    r, c = np.append(r, r[7]), np.append(c, c[7])         # two barcodes on one coordinate
+    r, c = np.append(r, r.max() + 40), np.append(c, c.max() + 40)   # a spot without neighbours (NA entry)
+    perm = rng.permutation(len(r))                        # spots are not stored in lattice order
+    r, c = r[perm].astype(np.int32), c[perm].astype(np.int32)
+    want, want_str = spec_numpy.find_neighbors_lattice(r, c, platform)
+    strings, (ptr, idx) = bsb.neighbors._find_neighbors(r, c, platform)
+    optr, oidx = oracle.lattice_neighbors(r, c, platform)
+    got, ogot = _lists(ptr, idx), _lists(optr, oidx)
+    assert len(got) == len(want) == len(ogot)
+    for j in range(len(want)):
+        assert np.array_equal(got[j], want[j]) and np.array_equal(ogot[j], want[j]), j
+    assert list(strings) == want_str
+    assert sum(s is None for s in want_str) >= 1            # isolated spots keep an NA entry / empty list
+
+
+def test_radius_neighbors_match_the_R_restatement(bsb, oracle):
+    import spec_numpy
+    rng = np.random.default_rng(9)
+    pos = np.round(rng.uniform(0, 12, size=(300, 2)), 1)     # ties at the radius occur on the 0.1 grid
+    for method, radius in (("manhattan", 1.5), ("euclidean", 1.3), ("manhattan", 0.05)):
+        want = spec_numpy.find_neighbors_radius(pos, radius, method)
+        got = bsb.find_neighbors(pos, radius, method)
+        ogot = oracle.find_neighbors(pos, radius, method)
+        for j in range(len(want)):
+            assert np.array_equal(np.asarray(got[j]), want[j]) and np.array_equal(np.asarray(ogot[j]), want[j]), (method, j)
+
+
+@pytest.mark.parametrize("platform,k", [("Visium", None), ("ST", 3), ("ST", 2)])
+def test_subspot_neighbors_match_the_cpp_restatement(bsb, oracle, platform, k):
+    """find_subspot_neighbors (src/cluster.cpp:161-215) including the candidate ORDER, which fixes df_j's columns."""
+    import spec_numpy
+    from bayesspace_b200 import synth
+    if platform == "Visium":
+        r, c = synth.hex_lattice(9, 8)
+        pos = np.c_[c.astype(float), r * np.sqrt(3.0)]
+        xd, yd = 1.0, np.sqrt(3.0)
+    else:
+        r, c = synth.square_lattice(8, 9)
+        pos = np.c_[c.astype(float), r.astype(float)]
+        xd, yd = 1.0, 1.0
+    _, (ptr, idx) = bsb.neighbors._find_neighbors(r, c, platform)
+    dc = synth.deconv_inputs(np.random.default_rng(0).normal(size=(len(r), 2)), pos, xd, yd,
+                             np.ones(len(r), dtype=np.int32), platform=platform,
+                             nsubspots_per_edge=k or 3)
+    want = spec_numpy.find_subspot_neighbors(_lists(ptr, idx), dc["positions2"], dc["dist"])
+    sp, si = bsb.find_subspot_neighbors((ptr, idx), dc["positions2"], dc["dist"])
+    op, oi = oracle.find_subspot_neighbors((ptr, idx), dc["positions2"], dc["dist"])
+    got, ogot = _lists(sp, si), _lists(op, oi)
+    for s in range(len(want)):
+        assert np.array_equal(got[s], want[s]) and np.array_equal(ogot[s], want[s]), s
