@@ -67,8 +67,10 @@ def sample_two(z_prev, z_new, p, u):
     return items[0][1] if u <= items[0][0] else items[1][1]
 
 
-def run(O, variant, Y, nbrs, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, seed):
-    """variant: 'iterate' | 'iterate_vvv' | 'iterate_t' | 'iterate_t_vvv'.  nbrs: list of 0-based neighbour arrays."""
+def run(O, variant, Y, nbrs, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, seed, order=None):
+    """variant: 'iterate' | 'iterate_vvv' | 'iterate_t' | 'iterate_t_vvv'.  nbrs: list of 0-based neighbour arrays.
+    order: visiting order of the z / w scan; None = the reference's j = 0..n-1 (the only departure from the reference
+    this file knows: the CUDA path visits colour class by colour class)."""
     tdist, vvv = variant in ("iterate_t", "iterate_t_vvv"), variant.endswith("vvv")
     nsnap = nrep // thin + 1
     zs = np.zeros((nsnap, n), dtype=np.int64)
@@ -112,7 +114,7 @@ def run(O, variant, Y, nbrs, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alp
         # ---- z (and w) scan (:272-306, :392-430, :507-553, :646-695)
         w_alpha = float((d + 4) // 2)             # integer division in the reference (quirk Q2)
         plj = np.zeros(n)
-        for j in range(n):
+        for j in (range(n) if order is None else order):
             z_prev = int(z[j])
             kp = z_prev - 1 if vvv else 0
             if tdist:
@@ -166,8 +168,9 @@ def adaptive_mcmc(acc, target, it, A, u):
 
 
 def run_deconv(O, Y, sub_nbrs, tdist, nrep, thin, n, n0, d, gamma, q, init, S, jitter_scale, adapt_before, c,
-               mu0, lambda0, alpha, beta, seed):
-    """Subspot s = r * n0 + j0.  sub_nbrs: 0-based neighbour arrays of the subspots."""
+               mu0, lambda0, alpha, beta, seed, order=None):
+    """Subspot s = r * n0 + j0.  sub_nbrs: 0-based neighbour arrays of the subspots.  order: visiting order of the
+    parent spots in the sequential accept / w / z section (None = the reference's j0 = 0..n0-1)."""
     Y = np.array(Y, dtype=np.float64)          # the reference mutates the caller's matrix; here a private copy
     Y0 = Y[:n0].copy()                          # :777
     nsnap = nrep // thin + 1
@@ -221,7 +224,7 @@ def run_deconv(O, Y, sub_nbrs, tdist, nrep, thin, n, n0, d, gamma, q, init, S, j
             Y_new[ss] = Yn
         # ---- accept / reject, RAM update, w, z (:969-1053)
         updates, ll = 0, np.zeros(n)
-        for j0 in range(n0):
+        for j0 in (range(n0) if order is None else order):
             ss = rows + j0
             u_y = O.uniform2(seed, P_SPOT_YACC, j0, i, 0)[0]
             if sample_two(0, 1, accp[j0], u_y) == 1:

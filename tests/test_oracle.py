@@ -301,3 +301,37 @@ def test_oracle_deconv_agrees_with_an_independent_numpy_restatement(oracle, tdis
     for r in range(nrep // thin + 1):
         assert np.allclose(np.asarray(got["lambda"][r]), np.asarray(ref["lambda"][r]), rtol=1e-8, atol=1e-12)
         assert np.allclose(got["Y"][r], np.asarray(ref["Y"][r]), rtol=1e-10, atol=1e-11)
+
+
+def test_chromatic_visiting_order_in_both_restatements(oracle):
+    """The GPU parity tests compare the CUDA chain with the oracle run in the CUDA path's visiting order (colour class
+    by colour class).  That order is the oracle's only extension of the reference; the independent restatement given
+    the same order must follow it step for step -- cluster sampler and deconvolution."""
+    import spec_numpy
+    from bayesspace_b200 import synth
+    w = synth.make_workload("tiny_hex")
+    ptr, idx = oracle.lattice_neighbors(w.array_row, w.array_col, w.platform)
+    col = (((w.array_col - 3 * w.array_row) // 2) % 3).astype(np.int32)      # closed-form 3-colouring of the hex lattice
+    assert all(col[j] != col[u] for j in range(w.n) for u in idx[ptr[j]:ptr[j + 1]])
+    order = np.lexsort((np.arange(w.n), col)).astype(np.int32)
+    nbrs = [idx[ptr[j]:ptr[j + 1]] for j in range(w.n)]
+    a = (7, 2, w.n, w.d, w.gamma, w.q, w.init)
+    ref = oracle.iterate_t(w.Y, (ptr, idx), *a, w.mu0, w.lambda0, w.alpha, w.beta, seed=5, order=order)
+    got = spec_numpy.run(oracle, "iterate_t", np.ascontiguousarray(w.Y), nbrs, *a, np.asarray(w.mu0),
+                         np.asarray(w.lambda0), w.alpha, w.beta, 5, order=order)
+    assert np.array_equal(got["z"], ref["z"]) and np.allclose(got["plogLik"][1:], ref["plogLik"][1:], rtol=1e-11)
+    seq = oracle.iterate_t(w.Y, (ptr, idx), *a, w.mu0, w.lambda0, w.alpha, w.beta, seed=5)
+    assert not np.array_equal(seq["z"], ref["z"])          # the order does matter: it is a different (valid) scan
+    # deconvolution: parents in colour order
+    pos = np.c_[w.array_col.astype(float), w.array_row * np.sqrt(3.0)]
+    dc = synth.deconv_inputs(w.Y, pos, 1.0, np.sqrt(3.0), w.truth, platform="Visium")
+    strings = synth.neighbor_strings(ptr, idx)
+    refd = oracle.iterate_deconv(dc["positions2"], dc["dist"], strings, dc["Y2"], True, 13, 3, dc["n"], dc["n0"], w.d,
+                                 2.0, w.q, dc["init1"], dc["subspots"], False, 5.0, 0, dc["c"], w.mu0, w.lambda0,
+                                 w.alpha, w.beta, 1, seed=9, order=order)
+    sp, si = oracle.find_subspot_neighbors((ptr, idx), dc["positions2"], dc["dist"])
+    gotd = spec_numpy.run_deconv(oracle, dc["Y2"], [si[sp[s]:sp[s + 1]] for s in range(dc["n"])], True, 13, 3, dc["n"],
+                                 dc["n0"], w.d, 2.0, w.q, dc["init1"], dc["subspots"], 5.0, 0, dc["c"],
+                                 np.asarray(w.mu0), np.asarray(w.lambda0), w.alpha, w.beta, 9, order=order)
+    assert np.array_equal(gotd["z"], refd["z"]) and np.array_equal(gotd["Ychange"][1:], refd["Ychange"][1:])
+    assert np.allclose(gotd["plogLik"][1:], refd["plogLik"][1:], rtol=1e-11)
