@@ -17,6 +17,7 @@
 
 #include "comm.hpp"
 #include "shard.hpp"
+#include "tma_maps.hpp"
 
 namespace bsb {
 
@@ -41,6 +42,73 @@ KernelRegistrar::KernelRegistrar(int d, const KernelsForD &k) {
   if (k.loglik) t.loglik = k.loglik;
   if (k.deconv) { t.deconv = k.deconv; t.deconv_smem = k.deconv_smem; }
 }
+FastRegistrar::FastRegistrar(int d, void (*launch)(int, const SweepArgs &, int, cudaStream_t),
+                             size_t (*smem)(int, const SweepArgs &)) {
+  kernel_table()[d].sweep_fast = launch;
+  kernel_table()[d].sweep_fast_smem = smem;
+}
+static bool use_fast(const KernelsForD &K, int vvv, const SweepArgs &a) {
+  static const bool off = std::getenv("BSB200_NO_FAST_SWEEP") != nullptr;   // A/B switch for measurements
+  return K.sweep_fast && a.maps && !vvv && a.PL.q <= kFastMaxQ && !off;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libbsb200.so does not link libcuda).
+int encode_sweep_maps(const double *Y, int64_t ld, int d, const int32_t *ell, int maxdeg, const int32_t *orig,
+                      SweepMaps *out, const char **msg) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+      *msg = "cuTensorMapEncodeTiled is not available from this driver";
+      return 1;
+    }
+    encode = (encode_fn) fn;
+  }
+  std::memset(out, 0, sizeof(*out));
+  const cuuint32_t ones[2] = {1, 1};
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t) ld, (cuuint64_t) d}, strides[1] = {(cuuint64_t) ld * sizeof(double)};
+    const cuuint32_t box[2] = {16, (cuuint32_t) d};
+    if (encode(&out->y, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(Y), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      *msg = "tensor map of Y";
+      return 1;
+    }
+  }
+  if (ell && maxdeg > 0) {
+    const cuuint64_t dims[2] = {(cuuint64_t) ld, (cuuint64_t) maxdeg}, strides[1] = {(cuuint64_t) ld * sizeof(int32_t)};
+    const cuuint32_t box[2] = {32, (cuuint32_t) maxdeg};
+    if (encode(&out->ell, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t *>(ell), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      *msg = "tensor map of the neighbour ids";
+      return 1;
+    }
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t) ld, 1}, strides[1] = {(cuuint64_t) ld * sizeof(int32_t)};
+    const cuuint32_t box[2] = {32, 1};
+    if (encode(&out->orig, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t *>(orig), dims, strides, box, ones,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      *msg = "tensor map of the original ids";
+      return 1;
+    }
+  }
+  return 0;
+}
+void launch_sweep_any(const KernelsForD &K, int tdist, int vvv, const SweepArgs &a, int grid, cudaStream_t s) {
+  if (use_fast(K, vvv, a)) K.sweep_fast(tdist, a, grid, s);
+  else K.sweep(tdist, vvv, a, grid, s);
+}
+size_t sweep_smem_any(const KernelsForD &K, int tdist, int vvv, const SweepArgs &a) {
+  return use_fast(K, vvv, a) ? K.sweep_fast_smem(tdist, a) : K.sweep_smem(tdist, vvv, a);
+}
 
 int select_device(int device) {
   int count = 0;
@@ -62,18 +130,21 @@ int select_device(int device) {
 // order so that every group's partial records are contiguous.  Groups are global (virtual shards).
 // ------------------------------------------------------------------------------------------------
 int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups_total, int seg_spots, int g0, int g1,
-                     int64_t lo, int64_t hi) {
+                     int64_t lo, int64_t hi, int align) {
   if (g1 < 0) { g0 = 0; g1 = ngroups_total; lo = 0; hi = n; }
+  if (align < 1) align = 1;
   ncol = ncolours;
   ngroups = g1 - g0;
   const int64_t n_own = hi - lo;
-  perm.resize((size_t) n_own);
-  inv.resize((size_t) n_own);
-  std::vector<int64_t> bucket((size_t) ngroups * ncol + 1, 0);
+  const size_t nb = (size_t) ngroups * ncol;
+  std::vector<int64_t> cnt(nb, 0), start(nb + 1, 0);
   auto grp = [&](int64_t j) { return (int) ((j * (int64_t) ngroups_total) / n) - g0; };
-  for (int64_t j = lo; j < hi; j++) bucket[(size_t) grp(j) * ncol + colour[j] + 1]++;
-  for (size_t b = 0; b < bucket.size() - 1; b++) bucket[b + 1] += bucket[b];
-  std::vector<int64_t> fill(bucket.begin(), bucket.end() - 1);
+  for (int64_t j = lo; j < hi; j++) cnt[(size_t) grp(j) * ncol + colour[j]]++;
+  for (size_t b = 0; b < nb; b++) start[b + 1] = (start[b] + cnt[b] + align - 1) / align * align;
+  npos = nb ? start[nb - 1] + cnt[nb - 1] : 0;
+  perm.assign((size_t) npos, -1);
+  inv.resize((size_t) n_own);
+  std::vector<int64_t> fill(start.begin(), start.end() - 1);
   for (int64_t j = lo; j < hi; j++) {
     const int64_t pos = fill[(size_t) grp(j) * ncol + colour[j]]++;
     perm[(size_t) pos] = (int32_t) j;
@@ -88,7 +159,7 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
   for (int g = 0; g < ngroups; g++) {
     group_start[(size_t) g] = slot;
     for (int c = 0; c < ncol; c++) {
-      const int64_t b = bucket[(size_t) g * ncol + c], e = bucket[(size_t) g * ncol + c + 1];
+      const int64_t b = start[(size_t) g * ncol + c], e = b + cnt[(size_t) g * ncol + c];
       for (int64_t s = b; s < e; s += seg_spots) {
         cb[(size_t) c].push_back((int32_t) s);
         cc[(size_t) c].push_back((int32_t) std::min<int64_t>(seg_spots, e - s));
@@ -148,7 +219,7 @@ using namespace bsb;
 struct bsb200_chain {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int64_t n = 0, n_own = 0, ld = 0, lo = 0, hi = 0;
+  int64_t n = 0, n_own = 0, n_pos = 0, ld = 0, lo = 0, hi = 0;   // n_pos: internal positions of the own spots (holes included)
   int d = 0, q = 0, nl = 1, maxdeg = 0, G = 1;
   bool tdist = false, vvv = false;
   uint32_t compat = 0, sweep_flags = 0;
@@ -177,6 +248,8 @@ struct bsb200_chain {
   double setup_ms = 0;
   int comm_rc = 0;               // first NCCL failure seen while enqueuing (reported by the next sync point)
   double *gsum_p = nullptr;      // shard sums: own buffer, or the exported window of the peer transport
+  SweepMaps maps;                // TMA descriptors of Y / ell / orig
+  bool have_maps = false;
 
   ~bsb200_chain() {
     if (stream) cudaStreamSynchronize(stream);
@@ -194,6 +267,7 @@ struct bsb200_chain {
 
   SweepArgs sweep_args(int colour, uint32_t flags, uint32_t iter_add) const {
     SweepArgs a{};
+    a.maps = have_maps ? &maps : nullptr;
     a.Y = Y.p; a.ld = ld; a.z = z.p; a.w = w.p; a.ell = ell.p; a.maxdeg = maxdeg; a.orig = orig.p;
     const int s0 = colour < 0 ? 0 : ord.colour_seg_start[(size_t) colour];
     const int s1 = colour < 0 ? (int) ord.seg_begin.size() : ord.colour_seg_start[(size_t) colour + 1];
@@ -237,7 +311,7 @@ struct bsb200_chain {
   void enqueue_sweep(int colour, uint32_t flags, uint32_t iter_add, cudaStream_t s) {
     SweepArgs a = sweep_args(colour, flags, iter_add);
     if (a.nseg <= 0) return;
-    K.sweep(tdist, vvv, a, a.nseg, s);
+    launch_sweep_any(K, tdist, vvv, a, a.nseg, s);
     g_launches++;
   }
   // labels of the boundary spots of one colour travel to the ranks that hold them as ghosts
@@ -358,8 +432,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   mark("validate+shard plan");
   const ShardPlan &plan = ch->plan;
   ch->G = G; ch->lo = plan.lo; ch->hi = plan.hi; ch->n_own = plan.n_own();
-  const int64_t n_own = ch->n_own, n_local = plan.n_local();
-  ch->ld = (n_local + 31) / 32 * 32;
+  const int64_t n_own = ch->n_own;
 
   // ---- colouring (of the whole graph: every rank derives the same classes) ------------------------
   std::vector<int32_t> colour;
@@ -379,11 +452,13 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if (rc) return rc;
   }
   mark("colouring");
-  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol), plan.g0, plan.g1, plan.lo, plan.hi);
+  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol), plan.g0, plan.g1, plan.lo, plan.hi, kOrderAlign);
   const SpotOrder &ord = ch->ord;
+  const int64_t n_pos = ch->n_pos = ord.npos;   // ghosts follow the own positions
+  ch->ld = (n_pos + (int64_t) plan.ghosts.size() + 31) / 32 * 32;
   mark("spot order");
   if (world > 1) {
-    rc = make_halo_plan(plan, a->nbr_ptr, a->nbr_idx, colour.data(), ncol, ord.inv, ch->halo);
+    rc = make_halo_plan(plan, a->nbr_ptr, a->nbr_idx, colour.data(), ncol, ord.inv, n_pos, ch->halo);
     if (rc) return rc;
     mark("halo plan");
     rc = ch->comm.init(world, rank, a->comm_id);
@@ -409,27 +484,28 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   for (int64_t j = 0; j < n; j++) maxdeg = std::max<int>(maxdeg, (int) (a->nbr_ptr[j + 1] - a->nbr_ptr[j]));
   ch->maxdeg = maxdeg;
   {
-    std::vector<int32_t> ell((size_t) std::max(maxdeg, 1) * ch->ld, -1);
+    std::vector<int32_t> ell((size_t) std::max(maxdeg, 1) * ch->ld + kSweepPad, -1);
     std::vector<uint8_t> z0((size_t) ch->ld, 0);
-    for (int64_t i = 0; i < n_own; i++) {
+    for (int64_t i = 0; i < n_pos; i++) {
       const int64_t j = ord.perm[(size_t) i];
+      if (j < 0) continue;   // hole
       z0[(size_t) i] = (uint8_t) (a->init[j] - 1);
       int e = 0;
       for (int64_t p = a->nbr_ptr[j]; p < a->nbr_ptr[j + 1]; p++, e++) {
         const int32_t u = a->nbr_idx[p];
         int32_t pos;
         if (u >= plan.lo && u < plan.hi) pos = ord.inv[(size_t) (u - plan.lo)];
-        else pos = (int32_t) (n_own + (std::lower_bound(plan.ghosts.begin(), plan.ghosts.end(), u) - plan.ghosts.begin()));
+        else pos = (int32_t) (n_pos + (std::lower_bound(plan.ghosts.begin(), plan.ghosts.end(), u) - plan.ghosts.begin()));
         ell[(size_t) e * ch->ld + i] = pos;
       }
     }
-    for (size_t gi = 0; gi < plan.ghosts.size(); gi++) z0[(size_t) n_own + gi] = (uint8_t) (a->init[plan.ghosts[gi]] - 1);
+    for (size_t gi = 0; gi < plan.ghosts.size(); gi++) z0[(size_t) n_pos + gi] = (uint8_t) (a->init[plan.ghosts[gi]] - 1);
     if ((rc = upload(ch->ell, ell.data(), ell.size(), s))) return rc;
     if (ch->comm.peer()) CK(cudaMemcpyAsync(ch->z.p, z0.data(), z0.size(), cudaMemcpyHostToDevice, s));
     else if ((rc = upload(ch->z, z0.data(), z0.size(), s))) return rc;
-    std::vector<int32_t> origp((size_t) ch->ld, 0);
+    std::vector<int32_t> origp((size_t) ch->ld + kSweepPad, -1);
     std::copy(ord.perm.begin(), ord.perm.end(), origp.begin());
-    std::copy(plan.ghosts.begin(), plan.ghosts.end(), origp.begin() + n_own);
+    std::copy(plan.ghosts.begin(), plan.ghosts.end(), origp.begin() + n_pos);
     if ((rc = upload(ch->orig, origp.data(), origp.size(), s))) return rc;
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }
@@ -457,12 +533,12 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     DevBuf<double> Yraw, gcol;
     DevBuf<int64_t> glo;
     if ((rc = Yraw.alloc((size_t) n_own * d)) || (rc = gcol.alloc((size_t) G * d)) || (rc = ch->ybar.alloc((size_t) d)) ||
-        (rc = ch->Y.alloc((size_t) d * ch->ld)))
+        (rc = ch->Y.alloc((size_t) d * ch->ld + kSweepPad)))
       return rc;
     CK(cudaMemcpy2DAsync(Yraw.p, sizeof(double) * n_own, a->Y + plan.lo, sizeof(double) * n, sizeof(double) * n_own, (size_t) d,
                          cudaMemcpyHostToDevice, s));
     if ((rc = upload(glo, plan.group_lo.data(), plan.group_lo.size(), s))) return rc;
-    CK(cudaMemsetAsync(ch->Y.p, 0, sizeof(double) * d * ch->ld, s));
+    CK(cudaMemsetAsync(ch->Y.p, 0, sizeof(double) * ((size_t) d * ch->ld + kSweepPad), s));
     CK(cudaMemsetAsync(gcol.p, 0, sizeof(double) * G * d, s));
     launch_colsums_groups(Yraw.p, n_own, glo.p, plan.lo, d, plan.g0, plan.g1 - plan.g0, gcol.p, s);
     if (world > 1 && !ch->comm.peer() && (rc = ch->comm.allgather_f64(gcol.p, (size_t) (plan.g1 - plan.g0) * d, s))) return rc;
@@ -481,7 +557,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
       ch->ybar_host[(size_t) c] = acc / (double) n;
     }
     CK(cudaMemcpyAsync(ch->ybar.p, ch->ybar_host.data(), sizeof(double) * d, cudaMemcpyHostToDevice, s));
-    launch_permute_center(Yraw.p, n_own, n_own, d, ch->orig.p, ch->ybar.p, ch->Y.p, ch->ld, s, plan.lo);
+    launch_permute_center(Yraw.p, n_own, n_pos, d, ch->orig.p, ch->ybar.p, ch->Y.p, ch->ld, s, plan.lo);
     CK(cudaStreamSynchronize(s));
   }
   mark("Y upload+centre");
@@ -535,6 +611,12 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   CK(cudaMallocHost(&ch->h_snap_z, sizeof(int32_t) * std::max<int64_t>(n_own, 1)));
   CK(cudaMallocHost(&ch->h_snap_w, sizeof(double) * std::max<int64_t>(n_own, 1)));
 
+  {
+    const char *msg = "";
+    if (encode_sweep_maps(ch->Y.p, ch->ld, d, ch->ell.p, maxdeg, ch->orig.p, &ch->maps, &msg))
+      return fail(BSB200_ERR_CUDA, "cannot encode the TMA descriptors (%s)", msg);
+    ch->have_maps = true;
+  }
   mark("buffers");
   // ---- statistics of the initial state -----------------------------------------------------------
   param_kernel_init();
@@ -585,7 +667,7 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     if (boundary) {
       const int64_t row = (ch->iters_done + 1) / ch->thin;
       const bool want_w = ch->tdist && (!out || out->weights);
-      launch_snapshot(ch->z.p, want_w ? ch->w.p : nullptr, ch->orig.p, ch->n_own, ch->snap_z.p,
+      launch_snapshot(ch->z.p, want_w ? ch->w.p : nullptr, ch->orig.p, ch->n_pos, ch->snap_z.p,
                       want_w ? ch->snap_w.p : nullptr, s, ch->lo);
       if (out && out->z_mode && row >= out->mode_from && row < ch->nrep / ch->thin + 1) {
         if (!ch->mode_cnt.p) {
@@ -721,7 +803,7 @@ int bsb200_chain_state(bsb200_chain *ch, int32_t *z, double *weights, double *mu
   cudaStream_t s = ch->stream;
   const int q = ch->q, d = ch->d;
   if (z || weights) {   // own spots only; entries of other ranks are left untouched
-    launch_snapshot(ch->z.p, ch->w.p, ch->orig.p, ch->n_own, ch->snap_z.p, ch->snap_w.p, s, ch->lo);
+    launch_snapshot(ch->z.p, ch->w.p, ch->orig.p, ch->n_pos, ch->snap_z.p, ch->snap_w.p, s, ch->lo);
     if (z) CK(cudaMemcpyAsync(z + ch->lo, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
     if (weights) CK(cudaMemcpyAsync(weights + ch->lo, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
   }
@@ -760,7 +842,7 @@ int bsb200_chain_dry_sweep(bsb200_chain *ch, int32_t *z_new, double *w_new, doub
   for (int c = 0; c < ch->ord.ncol; c++) {
     SweepArgs a = ch->sweep_args(c, SW_DRY, 0);
     a.dry_znew = dz.p; a.dry_w = dw.p; a.dry_hp = dhp.p; a.dry_hn = dhn.p; a.dry_prob = dpr.p; a.dry_acc = da.p;
-    if (a.nseg > 0) { ch->K.sweep(ch->tdist, ch->vvv, a, a.nseg, s); g_launches++; }
+    if (a.nseg > 0) { launch_sweep_any(ch->K, ch->tdist, ch->vvv, a, a.nseg, s); g_launches++; }
   }
   // roll the chain back: parameters and iteration counter as before (the statistics were not touched)
   CK(cudaMemcpyAsync(ch->params.p, params_keep.p, sizeof(double) * ch->PL.total, cudaMemcpyDeviceToDevice, s));

@@ -38,17 +38,20 @@ struct DevBuf {
 // Internal spot order and the segment / slot / group tables derived from it (chain.cu).
 struct SpotOrder {
   int ncol = 0, ngroups = 1, nslots = 0;
-  std::vector<int32_t> perm;   // internal position -> original spot
+  int64_t npos = 0;            // internal positions, holes included (every (shard, colour) range starts at a multiple of `align`)
+  std::vector<int32_t> perm;   // internal position -> original spot, -1 = hole
   std::vector<int32_t> inv;    // original spot -> internal position
   std::vector<int32_t> seg_begin, seg_count, seg_slot;   // launch lists, colour-major
   std::vector<int32_t> colour_seg_start;                 // ncol + 1 offsets into the launch lists
   std::vector<int32_t> group_start;                      // ngroups + 1 offsets into the slots
   // spots [lo, hi) = virtual shards [g0, g1) of ngroups_total; defaults: everything
+  // align: first position of every (shard, colour) range (TMA boxes of k_sweep_fast start at 16-byte boundaries)
   int build(int64_t n, const int32_t *colour, int ncolours, int ngroups_total, int seg_spots, int g0 = 0, int g1 = -1,
-            int64_t lo = 0, int64_t hi = 0);
+            int64_t lo = 0, int64_t hi = 0, int align = 1);
 };
 
 int select_device(int device);
+constexpr int kOrderAlign = 32;   // alignment of the ranges in the cluster samplers' internal order
 int choose_groups(int64_t n);
 int choose_segment(int64_t n, int ncol = 0);   // ncol = 0: the plain n-based rule (probes, deconvolution)
 void param_kernel_init();

@@ -29,11 +29,22 @@ struct KernelsForD {
   void (*loglik)(const LoglikArgs &a, cudaStream_t s);
   void (*deconv)(const DeconvArgs &a, int grid, cudaStream_t s);
   size_t (*deconv_smem)(const DeconvArgs &a);
+  // k_sweep_fast (sweep_fast.cu): shared precision, q <= kFastMaxQ
+  void (*sweep_fast)(int tdist, const SweepArgs &a, int grid, cudaStream_t s);
+  size_t (*sweep_fast_smem)(int tdist, const SweepArgs &a);
 };
+constexpr int kFastMaxQ = 16;
+constexpr int kSweepPad = 64;   // elements every array a sweep streams is over-allocated by (bulk copies read whole runs)
 KernelsForD *kernel_table();   // kMaxD + 1 entries, index = d; null pointers where not built
 struct KernelRegistrar {
   KernelRegistrar(int d, const KernelsForD &k);
 };
+struct FastRegistrar {
+  FastRegistrar(int d, void (*launch)(int, const SweepArgs &, int, cudaStream_t), size_t (*smem)(int, const SweepArgs &));
+};
+// Picks the sweep kernel for (model, precision, q) and launches it.
+void launch_sweep_any(const KernelsForD &K, int tdist, int vvv, const SweepArgs &a, int grid, cudaStream_t s);
+size_t sweep_smem_any(const KernelsForD &K, int tdist, int vvv, const SweepArgs &a);
 
 void launch_param(const ParamArgs &a, cudaStream_t stream);
 

@@ -89,7 +89,10 @@ enum SweepFlags : uint32_t {
   SW_NO_PAIRS = 8u     // skip the y y^T accumulation (normal model, shared precision)
 };
 
+struct SweepMaps;   // tma_maps.hpp
+
 struct SweepArgs {
+  const SweepMaps *maps;      // host pointer: TMA descriptors of Y / ell / orig (k_sweep_fast), may be null
   const double *Y;
   int64_t ld;
   uint8_t *z;

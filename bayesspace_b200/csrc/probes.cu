@@ -4,6 +4,7 @@
 
 #include "chain.hpp"
 #include "rng.cuh"
+#include "tma_maps.hpp"
 
 namespace bsb {
 
@@ -105,8 +106,8 @@ int bsb200_eval_suffstats(int32_t device, const double *Y, int64_t n, int32_t d,
   // Same staging as a chain: centred Y in identity order, one colour, the chain's segmentation.
   std::vector<int32_t> colour((size_t) n, 0);
   SpotOrder ord;
-  ord.build(n, colour.data(), 1, choose_groups(n), choose_segment(n));
-  const int64_t ld = (n + 31) / 32 * 32;
+  ord.build(n, colour.data(), 1, choose_groups(n), choose_segment(n), 0, -1, 0, 0, kOrderAlign);
+  const int64_t ld = (ord.npos + 31) / 32 * 32;
   const StatLayout SL = make_stat_layout(q, d, nl);
   const ParamLayout PL = make_param_layout(q, d, nl);
   DevBuf<double> dYraw, dY, dw, dybar, dpart, dgsum, dstats, dmu, dS, dparams, dplog;
@@ -114,26 +115,28 @@ int bsb200_eval_suffstats(int32_t device, const double *Y, int64_t n, int32_t d,
   DevBuf<int32_t> dorig, dsb, dsc, dss, dgs;
   DevBuf<uint32_t> diter;
   DevBuf<int> derr;
-  if ((rc = dYraw.alloc((size_t) n * d)) || (rc = dY.alloc((size_t) d * ld)) || (rc = dw.alloc((size_t) ld)) ||
+  if ((rc = dYraw.alloc((size_t) n * d)) || (rc = dY.alloc((size_t) d * ld + kSweepPad)) || (rc = dw.alloc((size_t) ld)) ||
       (rc = dybar.alloc((size_t) d)) || (rc = dpart.alloc((size_t) ord.nslots * SL.E)) ||
       (rc = dgsum.alloc((size_t) ord.ngroups * SL.E)) || (rc = dstats.alloc((size_t) SL.E)) ||
       (rc = dmu.alloc((size_t) q * d)) || (rc = dS.alloc((size_t) nl * d * d)) || (rc = dparams.alloc((size_t) PL.total)) ||
-      (rc = dplog.alloc(4)) || (rc = dz.alloc((size_t) ld)) || (rc = dorig.alloc((size_t) ld)) ||
+      (rc = dplog.alloc(4)) || (rc = dz.alloc((size_t) ld)) || (rc = dorig.alloc((size_t) ld + kSweepPad)) ||
       (rc = dsb.alloc(ord.seg_begin.size())) || (rc = dsc.alloc(ord.seg_begin.size())) ||
       (rc = dss.alloc(ord.seg_begin.size())) || (rc = dgs.alloc(ord.group_start.size())) || (rc = diter.alloc(1)) ||
       (rc = derr.alloc(1)))
     return rc;
   std::vector<uint8_t> z0((size_t) ld, 0);
   std::vector<double> w0((size_t) ld, 1.0);
-  std::vector<int32_t> orig((size_t) ld, 0);
+  std::vector<int32_t> orig((size_t) ld, -1);
   for (int64_t j = 0; j < n; j++) {
-    z0[(size_t) j] = (uint8_t) (z[j] - 1);
-    if (w) w0[(size_t) j] = w[j];
-    orig[(size_t) j] = (int32_t) j;
+    const size_t pos = (size_t) ord.inv[(size_t) j];
+    z0[pos] = (uint8_t) (z[j] - 1);
+    if (w) w0[pos] = w[j];
+    orig[pos] = (int32_t) j;
   }
   CK(cudaMemset(derr.p, 0, sizeof(int)));
   CK(cudaMemset(diter.p, 0, sizeof(uint32_t)));
-  CK(cudaMemset(dY.p, 0, sizeof(double) * d * ld));
+  CK(cudaMemset(dY.p, 0, sizeof(double) * ((size_t) d * ld + kSweepPad)));
+  CK(cudaMemset(dorig.p, 0, sizeof(int32_t) * ((size_t) ld + kSweepPad)));
   CK(cudaMemcpy(dYraw.p, Y, sizeof(double) * n * d, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dz.p, z0.data(), (size_t) ld, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw.p, w0.data(), sizeof(double) * ld, cudaMemcpyHostToDevice));
@@ -143,18 +146,25 @@ int bsb200_eval_suffstats(int32_t device, const double *Y, int64_t n, int32_t d,
   CK(cudaMemcpy(dss.p, ord.seg_slot.data(), sizeof(int32_t) * ord.seg_slot.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dgs.p, ord.group_start.data(), sizeof(int32_t) * ord.group_start.size(), cudaMemcpyHostToDevice));
   launch_colmeans(dYraw.p, n, d, dybar.p, 0);
-  launch_permute_center(dYraw.p, n, n, d, dorig.p, dybar.p, dY.p, ld, 0);
+  launch_permute_center(dYraw.p, n, ord.npos, d, dorig.p, dybar.p, dY.p, ld, 0);
   std::vector<double> ybar((size_t) d), muc((size_t) q * d);
   CK(cudaMemcpy(ybar.data(), dybar.p, sizeof(double) * d, cudaMemcpyDeviceToHost));
   for (int k = 0; k < q; k++)
     for (int c = 0; c < d; c++) muc[(size_t) k * d + c] = mu[k * d + c] - ybar[(size_t) c];
   CK(cudaMemcpy(dmu.p, muc.data(), sizeof(double) * q * d, cudaMemcpyHostToDevice));
+  SweepMaps maps;
+  {
+    const char *msg = "";
+    if (encode_sweep_maps(dY.p, ld, d, nullptr, 0, dorig.p, &maps, &msg))
+      return fail(BSB200_ERR_CUDA, "cannot encode the TMA descriptors (%s)", msg);
+  }
   SweepArgs a{};
+  a.maps = &maps;
   a.Y = dY.p; a.ld = ld; a.z = dz.p; a.w = dw.p; a.ell = nullptr; a.maxdeg = 0; a.orig = dorig.p;
   a.seg_begin = dsb.p; a.seg_count = dsc.p; a.seg_slot = dss.p; a.nseg = (int) ord.seg_begin.size();
   a.params = dparams.p; a.PL = PL; a.partials = dpart.p; a.SL = SL; a.iter = diter.p; a.flags = SW_STATS_ONLY;
   a.err = derr.p;
-  K.sweep(1, nl > 1 ? 1 : 0, a, a.nseg, 0);
+  launch_sweep_any(K, 1, nl > 1 ? 1 : 0, a, a.nseg, 0);
   g_launches++;
   ParamArgs p{};
   p.PL = PL; p.SL = SL; p.params = dparams.p; p.partials = dpart.p; p.group_start = dgs.p; p.ngroups = ord.ngroups;

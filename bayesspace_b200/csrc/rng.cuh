@@ -120,4 +120,65 @@ __device__ __forceinline__ int propose_label(int z_prev, int q, double u) {
   return (t < z_prev) ? t : t + 1;
 }
 
+// ---- per-spot draws of the cluster samplers' z / w scan --------------------------------------------------------
+// ONE Philox block per spot and iteration, counter (spot, 0, iteration, P_SPOT_U), serves the three uniforms of
+// the scan: word 0 -> the proposal (sample(qlessk, 1), src/cluster.cpp:278), words 1..2 -> the 53-bit uniform of
+// the accept step (sample(.., prob), :304), word 3 -> the uniform of the first Marsaglia-Tsang attempt of the
+// t-model weight (R::rgamma, :518).  The normal of attempt t comes from block (spot, t, iteration, P_SPOT_GAMMA);
+// attempts t >= 1 (rare) take their uniform from word 0 of block (spot, 0x40000000 + t, ..).
+__device__ __forceinline__ double u32c(uint32_t x) { return ((double) x + 0.5) * (1.0 / 4294967296.0); }
+
+__device__ __forceinline__ void rng_spot(Key key, uint32_t index, uint32_t iter, uint32_t &prop_bits, double &u_acc,
+                                         double &u_sq) {
+  const uint4 o = philox4x32_10(index, 0u, iter, P_SPOT_U, key);
+  prop_bits = o.x;
+  u_acc = u53(o.y, o.z);
+  u_sq = u32c(o.w);
+}
+
+// sample(qlessk, 1) from 32 random bits: element floor((q-1) * bits / 2^32) of the labels without the current one.
+__device__ __forceinline__ int propose_label_bits(int z_prev, int q, uint32_t bits) {
+  const int t = (int) __umulhi(bits, (uint32_t) (q - 1));
+  return (t < z_prev) ? t : t + 1;
+}
+
+// Accept step of sample({z, z'}, 1, TRUE, {1 - p, p}) with p = min(1, exp(delta)), decided in the log domain:
+// with v = u (p >= 1/2) or 1 - u (p < 1/2) the rule of sample_two() reads log v <= delta resp. log v < delta.
+// A single-precision logarithm decides whenever its error bound cannot change the answer; the (rare) ambiguous
+// cases evaluate exp(delta) and sample_two() exactly as the reference's arithmetic does.
+__device__ __forceinline__ bool mh_accept(double delta, double u) {
+  if (delta >= 0.0) return true;
+  const double v = (delta >= -0.69314718055994530942) ? u : 1.0 - u;
+  const float lf = __logf((float) v);
+  const double gap = delta - (double) lf;
+  if (fabs(gap) > 1e-4 * (1.0 + fabs((double) lf))) return gap > 0.0;
+  return sample_two(exp(delta), u);
+}
+
+// Gamma(shape >= 1, scale) for the t-model weights (Marsaglia & Tsang), draws laid out as described above.
+// The second acceptance test, log u < x^2/2 + d (1 - v + log v), is screened in single precision the same way.
+__device__ __forceinline__ double rng_gamma_spot(Key key, uint32_t index, uint32_t iter, double shape, double scale,
+                                                 double u_first) {
+  if (!(shape >= 1.0) || !(scale > 0.0)) return __longlong_as_double(0x7ff8000000000000ll);
+  const double dd = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+  for (uint32_t t = 0; t < 0x3fffffffu; t++) {
+    const double x = rng_normal_first(key, P_SPOT_GAMMA, index, iter, t);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = u_first;
+    if (t) u = u32c(philox4x32_10(index, 0x40000000u + t, iter, P_SPOT_GAMMA, key).x);
+    const double x2 = x * x;
+    bool ok = u < 1.0 - 0.0331 * x2 * x2;
+    if (!ok) {
+      const float lu = __logf((float) u), lv = __logf((float) v);
+      const double gap = (0.5 * x2 + dd * ((1.0 - v) + (double) lv)) - (double) lu;
+      if (fabs(gap) > 1e-4 * (1.0 + fabs((double) lu) + dd * (1.0 + fabs((double) lv)))) ok = gap > 0.0;
+      else ok = log(u) < 0.5 * x2 + dd * (1.0 - v + log(v));
+    }
+    if (ok) return dd * v * scale;
+  }
+  return __longlong_as_double(0x7ff8000000000000ll);
+}
+
 }   // namespace bsb

@@ -33,13 +33,13 @@ int make_shard_plan(int64_t n, const int64_t *ptr, const int32_t *idx, int group
 }
 
 int make_halo_plan(const ShardPlan &plan, const int64_t *ptr, const int32_t *idx, const int32_t *colour, int ncol,
-                   const std::vector<int32_t> &own_inv, HaloPlan &halo) {
+                   const std::vector<int32_t> &own_inv, int64_t ghost_base, HaloPlan &halo) {
   const int W = plan.world;
   std::vector<std::vector<int32_t>> send((size_t) ncol * W), recv((size_t) ncol * W);
   // what I receive: my ghosts, by (colour, owner), ascending original id (ghosts are sorted)
   for (size_t gi = 0; gi < plan.ghosts.size(); gi++) {
     const int32_t u = plan.ghosts[gi];
-    recv[(size_t) colour[u] * W + plan.owner(u)].push_back((int32_t) (plan.n_own() + (int64_t) gi));
+    recv[(size_t) colour[u] * W + plan.owner(u)].push_back((int32_t) (ghost_base + (int64_t) gi));
   }
   // what I send: own spots read by a spot of another rank
   std::vector<std::vector<int32_t>> need((size_t) W);
@@ -91,7 +91,7 @@ extern "C" int bsb200_shard_plan(const int64_t *ptr, const int32_t *idx, int64_t
     std::vector<int32_t> own_inv((size_t) plan.n_own());
     for (int64_t j = 0; j < plan.n_own(); j++) own_inv[(size_t) j] = (int32_t) j;   // identity: positions = original id - lo
     HaloPlan halo;
-    rc = make_halo_plan(plan, ptr, idx, colour, ncolours, own_inv, halo);
+    rc = make_halo_plan(plan, ptr, idx, colour, ncolours, own_inv, plan.n_own(), halo);
     if (rc) return rc;
     const int K = ncolours * world;
     if (counts)

@@ -41,6 +41,7 @@ int make_shard_plan(int64_t n, const int64_t *ptr, const int32_t *idx, int group
 // Send / receive lists per (colour, peer), both ordered by original id so that the two sides agree
 // without negotiation.  local_pos(j) maps an original id (own or ghost) to its local position.
 int make_halo_plan(const ShardPlan &plan, const int64_t *ptr, const int32_t *idx, const int32_t *colour, int ncol,
-                   const std::vector<int32_t> &own_inv /* original id - lo -> internal position */, HaloPlan &halo);
+                   const std::vector<int32_t> &own_inv /* original id - lo -> internal position */,
+                   int64_t ghost_base /* local position of the first ghost */, HaloPlan &halo);
 
 }   // namespace bsb

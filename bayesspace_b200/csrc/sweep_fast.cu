@@ -1,0 +1,445 @@
+// sweep_fast.cu -- k_sweep_fast<D, TDIST, NH>: the z / w sweep of the shared-precision samplers
+//   iterate    /root/reference/src/cluster.cpp:272-307      iterate_t  :507-553
+// for q <= 16 clusters (NH = ceil(q / 8) label tiles), one instantiation per dimension d = BSB_D.  It is the
+// kernel BASELINE.json's C2 / C4 / C5 configurations run; per-cluster precisions (iterate_vvv, iterate_t_vvv)
+// and q > 16 stay on k_sweep (sweep_kernels.cu).
+//
+// Same chromatic scan and the same arithmetic identities as k_sweep (factorise once per iteration, expanded
+// quadratic form, statistics of the next iteration fused into the sweep).  What is different is the machine
+// mapping, chosen from the round-1 ncu profile (the sweep was instruction-issue bound at 53 warp-instructions
+// per spot-update, not memory bound):
+//
+//  * every WARP is an independent worker with a private two-stage pipeline: 32 spots x (d PC columns,
+//    neighbour ids, original ids) arrive in its own shared-memory buffers through four TMA tensor copies
+//    (cp.async.bulk.tensor, tma_maps.hpp) issued by one lane and are awaited on the warp's own mbarrier.  There is
+//    no CTA barrier in the tile loop any more, and no per-thread cp.async address arithmetic;
+//  * the tile is never restaged: the pooled second moments sum_j w_j y_j y_j^T run on the FP64 tensor pipe
+//    (mma.sync.m8n8k4.f64) straight from the landing buffer as A = y, B = w . y (the weight is applied to the B
+//    fragment), the per-cluster sums as A = y, B = w . [z = k]; each warp folds its own 32 spots and keeps the
+//    output tiles in registers for the whole segment;
+//  * one Philox block per spot for proposal / accept / first gamma attempt (rng_spot), the MH accept and the
+//    second Marsaglia-Tsang test decided by a single-precision screen with an exact FP64 fallback (rng.cuh);
+//  * parameters are read from shared memory as 16-byte broadcasts; the Potts scale 2 gamma / |N_j| is a table;
+//    the neighbour loop is unrolled for the lattice degrees (4 and 6).
+#include "kernels.hpp"
+#include "pipeline.cuh"
+#include "rng.cuh"
+#include "tile_stats.cuh"
+#include "tma_maps.hpp"
+
+#ifndef BSB_D
+#error "compile with -DBSB_D=<d>"
+#endif
+
+namespace bsb {
+namespace {
+
+constexpr int kWarps = kBlock / 32;
+constexpr int kRowB = 128;   // bytes of one row of a Y box (16 spots) and of an ell / orig row (32 spots)
+
+// Shared-memory carve-up (byte offsets; the per-warp areas start at a 1024-byte boundary, which SWIZZLE_128B needs
+// for its pattern to be a function of the row index alone).
+struct FastSmem {
+  int g, c, gL, cL, PL, pot, acc, red, mbar, shared_bytes, warp_stride, ybox, ell, orig, wst, zst;
+  size_t bytes;
+};
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline FastSmem fast_smem_layout(int D, int q, int E, bool tdist, int nh, int maxdeg) {
+  FastSmem s;
+  const int DS = D + (D & 1), NP = D * (D + 1) / 2, DP = (D + 1 + 7) / 8 * 8;
+  int o = 0;
+  s.g = o; o += q * DS * 8;
+  s.gL = o; o += tdist ? q * DS * 8 : 0;
+  s.PL = o; o += tdist ? align16(NP * 8) : 0;
+  s.c = o; o += align16(q * 8);
+  s.cL = o; o += tdist ? align16(q * 8) : 0;
+  s.pot = o; o += align16((kMaxDeg + 1) * 8);
+  s.acc = o; o += align16(E * 8);
+  s.red = o; o += align16(3 * kWarps * 8);
+  s.mbar = o; o += kWarps * 2 * 8;
+  s.shared_bytes = (o + 1023) & ~1023;
+  int w = 0;
+  s.ybox = DP * kRowB;                 // one box: DP rows (d PCs, the constant-1 row, zero rows) of 16 spots
+  w += 4 * s.ybox;                     // [buffer][half]; also holds the warp's output tiles at the end of a segment
+  s.ell = w; w += 2 * maxdeg * kRowB;
+  s.orig = w; w += 2 * kRowB;
+  s.wst = w; w += 32 * 8;
+  s.zst = w; w += 32;
+  s.warp_stride = (w + 1023) & ~1023;
+  s.bytes = (size_t) s.shared_bytes + (size_t) kWarps * s.warp_stride + 1024;   // + slack to align the base
+  return s;
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int fast_min_blocks(int D) { return D <= 16 ? 4 : (D <= 24 ? 3 : 2); }
+
+// x^T P x with P = packed upper triangle (row-major, off-diagonals doubled), read as 16-byte broadcasts.
+template <int D>
+__device__ __forceinline__ double quadform2(const double (&y)[D], const double *__restrict__ P) {
+  constexpr int NP = D * (D + 1) / 2;
+  const double2 *P2 = reinterpret_cast<const double2 *>(P);
+  double s[D];
+#pragma unroll
+  for (int a = 0; a < D; a++) s[a] = 0.0;
+  int a = 0, b = 0;   // (a, b) of packed index p, advanced at compile time by the unroller
+#pragma unroll
+  for (int p2 = 0; p2 < (NP + 1) / 2; p2++) {
+    const double2 v = P2[p2];
+    s[a] = fma(v.x, y[b], s[a]);
+    if (++b == D) { a++; b = a; }
+    if (2 * p2 + 1 < NP) {
+      s[a] = fma(v.y, y[b], s[a]);
+      if (++b == D) { a++; b = a; }
+    }
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; r++) acc = fma(y[r], s[r], acc);
+  return acc;
+}
+
+// y . g with g padded to an even length and 16-byte aligned
+template <int D>
+__device__ __forceinline__ double dot2(const double (&y)[D], const double *__restrict__ g) {
+  const double2 *g2 = reinterpret_cast<const double2 *>(g);
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int c2 = 0; c2 < (D + 1) / 2; c2++) {
+    const double2 v = g2[c2];
+    s0 = fma(y[2 * c2], v.x, s0);
+    if (2 * c2 + 1 < D) s1 = fma(y[2 * c2 + 1], v.y, s1);
+  }
+  return s0 + s1;
+}
+
+// Potts counts over the neighbour ids of this lane's spot (rows of 32 ids, -1 = padding).
+template <int NB>
+__device__ __forceinline__ void potts_counts(const int32_t *__restrict__ ellrow, int nb_rows, const uint8_t *__restrict__ z,
+                                             int zk, int zn, int &deg, int &cp, int &cn) {
+  deg = cp = cn = 0;
+  if (NB > 0) {
+    int32_t nb[NB > 0 ? NB : 1];
+    int zu[NB > 0 ? NB : 1];
+#pragma unroll
+    for (int e = 0; e < NB; e++) nb[e] = e < nb_rows ? ellrow[e * 32] : -1;
+#pragma unroll
+    for (int e = 0; e < NB; e++) zu[e] = nb[e] >= 0 ? (int) z[nb[e]] : -1;
+#pragma unroll
+    for (int e = 0; e < NB; e++) {
+      deg += nb[e] >= 0;
+      cp += zu[e] == zk;
+      cn += zu[e] == zn;
+    }
+  } else {
+    for (int e = 0; e < nb_rows; e++) {
+      const int32_t nb = ellrow[e * 32];
+      if (nb >= 0) {
+        const int zu = z[nb];
+        deg++;
+        cp += zu == zk;
+        cn += zu == zn;
+      }
+    }
+  }
+}
+
+template <int D, bool TDIST, int NH>
+__global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
+    k_sweep_fast(const __grid_constant__ SweepArgs a, const __grid_constant__ SweepMaps maps) {
+  extern __shared__ __align__(1024) unsigned char smdyn[];
+  constexpr int NP = D * (D + 1) / 2, DS = D + (D & 1);
+  constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, DP = TileGeom<D>::DP;
+  constexpr int YBOX = DP * kRowB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = a.PL.q, E = a.SL.E;
+  const FastSmem L = fast_smem_layout(D, q, E, TDIST, NH, a.maxdeg);
+  unsigned char *smraw = smdyn + ((1024u - (smem_u32(smdyn) & 1023u)) & 1023u);   // 1024-byte aligned base
+  double *s_g = reinterpret_cast<double *>(smraw + L.g), *s_c = reinterpret_cast<double *>(smraw + L.c);
+  double *s_gL = reinterpret_cast<double *>(smraw + L.gL), *s_cL = reinterpret_cast<double *>(smraw + L.cL);
+  double *s_PL = reinterpret_cast<double *>(smraw + L.PL), *s_pot = reinterpret_cast<double *>(smraw + L.pot);
+  double *acc = reinterpret_cast<double *>(smraw + L.acc), *red = reinterpret_cast<double *>(smraw + L.red);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smraw + L.mbar) + 2 * warp;
+  unsigned char *wbase = smraw + L.shared_bytes + (size_t) warp * L.warp_stride;
+  unsigned char *ybuf = wbase;   // [buffer][half] boxes of DP rows x 128 bytes, SWIZZLE_128B
+  int32_t *well = reinterpret_cast<int32_t *>(wbase + L.ell), *worig = reinterpret_cast<int32_t *>(wbase + L.orig);
+  double *wst = reinterpret_cast<double *>(wbase + L.wst);
+  uint8_t *zst = wbase + L.zst;
+  double *cfold = reinterpret_cast<double *>(smraw + L.shared_bytes);   // + warp * warp_stride / 8
+  const int fold_stride = L.warp_stride / 8;
+
+  const bool stats_only = a.flags & SW_STATS_ONLY, dry = a.flags & SW_DRY;
+  if (*a.err) return;
+  if (!stats_only) {
+    const double *Pm = a.params;
+    for (int e = tid; e < q * DS; e += kBlock) {
+      const int k = e / DS, cc = e - k * DS;
+      s_g[e] = cc < D ? Pm[a.PL.g + k * D + cc] : 0.0;
+      if (TDIST) s_gL[e] = cc < D ? Pm[a.PL.gL + k * D + cc] : 0.0;
+    }
+    for (int e = tid; e < q; e += kBlock) {
+      s_c[e] = Pm[a.PL.c + e];
+      if (TDIST) s_cL[e] = Pm[a.PL.cL + e];
+    }
+    if (TDIST)
+      for (int e = tid; e < NP + (NP & 1); e += kBlock) s_PL[e] = e < NP ? Pm[a.PL.PL + e] : 0.0;
+    for (int e = tid; e <= kMaxDeg; e += kBlock) s_pot[e] = e ? a.gamma / e * 2 : 0.0;   // (gamma / |N_j|) * 2 as at :289
+  }
+  // constant rows of the four boxes: row D = 1 (its products give n_k and the sum of weights), rows beyond = 0
+  auto init_const_rows = [&]() {
+    for (int e = lane; e < 4 * (DP - D) * 16; e += 32) {
+      const int box = e / ((DP - D) * 16), r = e % ((DP - D) * 16);
+      reinterpret_cast<double *>(ybuf + box * YBOX + D * kRowB)[r] = r < 16 ? 1.0 : 0.0;
+    }
+  };
+  init_const_rows();
+  if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
+  mbar_fence_init();
+  fence_proxy_async();
+  __syncthreads();
+
+  const Key key{a.key0, a.key1};
+  const uint32_t it = *a.iter + a.iter_add;
+  constexpr double w_alpha = (double) ((D + 4) / 2);   // quirk Q2: integer division (src/cluster.cpp:508)
+  const double halfD = 0.5 * D;
+  const bool do_pairs = !(a.flags & SW_NO_PAIRS) && a.SL.nlT > 0;
+  const int ell_rows = stats_only ? 0 : a.maxdeg;
+  const uint32_t tx_bytes = (uint32_t) (2 * D * kRowB + (stats_only ? 0 : (ell_rows + 1) * kRowB));
+  uint32_t ntile = 0;   // sub-tiles this warp has consumed: buffer = ntile & 1, barrier parity = (ntile >> 1) & 1
+
+  // Swizzled addressing (SWIZZLE_128B: 16-byte chunk index XOR row mod 8).
+  //  per-spot reads: this lane's spot is column (lane & 15) of half (lane >> 4)
+  const int my_half = (lane >> 4) * YBOX, my_chunk = ((lane & 15) >> 1) << 4, my_lo = (lane & 1) << 3;
+  //  DMMA fragments: row 8 i + kc, spot 4 g + lq of the warp's 32
+  const int kc = lane >> 2, lq = lane & 3;
+  const int frag_row = kc * kRowB, frag_sw = ((lq >> 1) ^ kc) << 4, frag_lo = (lq & 1) << 3;
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const int begin = a.seg_begin[seg], count = a.seg_count[seg];
+    const int nsub = (count + 31) >> 5;
+    for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    double hp_acc = 0.0, nacc = 0.0, lw_m = 1.0;
+    int lw_e = 0;
+    double C[NTILES][2], CH[NT][NH][2];
+#pragma unroll
+    for (int t = 0; t < NTILES; t++) C[t][0] = C[t][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+#pragma unroll
+      for (int h = 0; h < NH; h++) CH[i][h][0] = CH[i][h][1] = 0.0;
+
+    auto issue = [&](int sub, int buf) {
+      if (lane == 0) {
+        const int gi = begin + 32 * sub;
+        mbar_arrive_expect_tx(mbar + buf, tx_bytes);
+        tma_load_2d(ybuf + (2 * buf) * YBOX, &maps.y, gi, 0, mbar + buf);
+        tma_load_2d(ybuf + (2 * buf + 1) * YBOX, &maps.y, gi + 16, 0, mbar + buf);
+        if (!stats_only) {
+          if (ell_rows) tma_load_2d(well + buf * ell_rows * 32, &maps.ell, gi, 0, mbar + buf);
+          tma_load_2d(worig + buf * 32, &maps.orig, gi, 0, mbar + buf);
+        }
+      }
+    };
+    if (warp < nsub) issue(warp, ntile & 1);
+
+    for (int sub = warp; sub < nsub; sub += kWarps, ntile++) {
+      const int cur = ntile & 1;
+      if (sub + kWarps < nsub) issue(sub + kWarps, cur ^ 1);
+      const int64_t j = (int64_t) begin + 32 * sub + lane;
+      const bool active = 32 * sub + lane < count;
+      const unsigned char *ycur = ybuf + 2 * cur * YBOX;
+      uint8_t zk8 = 255;
+      if (active) zk8 = a.z[j];
+      mbar_wait(mbar + cur, (ntile >> 1) & 1);
+
+      double wj = active ? 1.0 : 0.0;
+      int zfinal = zk8;
+      if (active) {
+        const int zk = zk8;
+        if (stats_only) {
+          if (TDIST) wj = a.w[j];
+        } else {
+          const uint32_t og = (uint32_t) worig[cur * 32 + lane];
+          uint32_t prop_bits;
+          double u_acc, u_sq;
+          rng_spot(key, og, it, prop_bits, u_acc, u_sq);
+          const int zn = propose_label_bits(zk, q, prop_bits);
+          int deg, cp, cn;
+          const int32_t *ellrow = well + cur * ell_rows * 32 + lane;
+          if (ell_rows <= 4) potts_counts<4>(ellrow, ell_rows, a.z, zk, zn, deg, cp, cn);
+          else if (ell_rows <= 6) potts_counts<6>(ellrow, ell_rows, a.z, zk, zn, deg, cp, cn);
+          else potts_counts<0>(ellrow, ell_rows, a.z, zk, zn, deg, cp, cn);
+          const double ps = s_pot[deg];
+          const double pot_p = ps * cp, pot_n = ps * cn;
+          double y[D];
+          {
+            const unsigned char *yb = ycur + my_half + my_lo;
+#pragma unroll
+            for (int c = 0; c < D; c++)
+              y[c] = *reinterpret_cast<const double *>(yb + c * kRowB + (my_chunk ^ ((c & 7) << 4)));
+          }
+          if (TDIST) {
+            // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518)
+            const double aL = quadform2<D>(y, s_PL);
+            const double bL = dot2<D>(y, s_gL + zk * DS);
+            const double quad = aL - 2.0 * bL + s_cL[zk];
+            wj = rng_gamma_spot(key, og, it, w_alpha, 2.0 / (quad + 4.0), u_sq);
+          }
+          const double lin_p = s_c[zk] - 2.0 * dot2<D>(y, s_g + zk * DS);
+          const double lin_n = s_c[zn] - 2.0 * dot2<D>(y, s_g + zn * DS);
+          // y^T M y and (d/2) log w_j are common to both labels: they only enter plogLik (statistics, lw)
+          const double delta = (pot_n - pot_p) - 0.5 * wj * (lin_n - lin_p);
+          const double hp_part = pot_p - 0.5 * wj * lin_p;
+          if (delta != delta) atomicExch(a.err, BSB_DEVERR_NUMERIC);   // NA probability (Rcpp sample() stops)
+          const bool accept = mh_accept(delta, u_acc);
+          if (dry) {
+            const double LOG2PI = 1.8378770664093454835606594728112;
+            const double logw = TDIST ? log(wj) : 0.0;
+            const double aM = quadform<D>(y, a.params + a.PL.PM), ld = a.params[a.PL.logdet];
+            double prob = exp(delta);
+            if (prob > 1.0) prob = 1.0;
+            a.dry_znew[og] = zn + 1;
+            a.dry_w[og] = wj;
+            a.dry_hp[og] = pot_p + ((ld - halfD * LOG2PI) + halfD * logw - 0.5 * wj * (aM + lin_p));
+            a.dry_hn[og] = pot_n + ((ld - halfD * LOG2PI) + halfD * logw - 0.5 * wj * (aM + lin_n));
+            a.dry_prob[og] = prob;
+            a.dry_acc[og] = accept ? 1 : 0;
+          } else {
+            if (accept) {
+              a.z[j] = (uint8_t) zn;
+              zfinal = zn;
+              nacc += 1.0;
+            }
+            if (TDIST) {
+              a.w[j] = wj;
+              // sum_j log w_j as a running product, renormalised only when it leaves [1e-150, 1e150]
+              double m2 = lw_m * wj;
+              if (!(m2 >= 1e-150 && m2 <= 1e150)) {
+                int e1, e2;
+                const double f1 = frexp(lw_m, &e1), f2 = frexp(wj, &e2);
+                m2 = f1 * f2;
+                lw_e += e1 + e2;
+              }
+              lw_m = m2;
+            }
+            hp_acc += hp_part;
+          }
+        }
+      }
+      if (!dry) {
+        // ---- fold this warp's 32 spots into its output tiles (FP64 tensor pipe) ---------------------
+        wst[lane] = wj;
+        zst[lane] = (uint8_t) zfinal;
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+          // spot 4 g + lq: half g >> 2, column 4 (g & 3) + lq, i.e. chunk 2 (g & 3) + (lq >> 1)
+          const unsigned char *fb = ycur + (g >> 2) * YBOX + frag_row + (frag_sw ^ ((g & 3) << 5)) + frag_lo;
+          double f[NT];
+#pragma unroll
+          for (int i = 0; i < NT; i++) f[i] = *reinterpret_cast<const double *>(fb + i * 8 * kRowB);
+          const double wt = wst[4 * g + lq];
+          const int zt = zst[4 * g + lq];
+          if (do_pairs) {
+            double b[NT];
+#pragma unroll
+            for (int i = 0; i < NT; i++) b[i] = f[i] * wt;
+            int tix = 0;
+#pragma unroll
+            for (int i = 0; i < NT; i++)
+#pragma unroll
+              for (int jj = i; jj < NT; jj++) dmma_m8n8k4(C[tix++], f[i], b[jj]);
+          }
+#pragma unroll
+          for (int h = 0; h < NH; h++) {
+            const double hv = zt == kc + 8 * h ? wt : 0.0;
+#pragma unroll
+            for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][h], f[i], hv);
+          }
+        }
+      }
+      __syncwarp();   // the buffer and the staging rows may be refilled from here on
+    }
+    if (dry) continue;
+    // ---- fold warps in a fixed order and publish the segment's record ------------------------------------
+    double lws = TDIST ? log(lw_m) + (double) lw_e * 0.69314718055994530942 : 0.0;
+    {
+      // this warp's buffers are idle (all of its copies have been consumed): they now carry its output tiles
+      double2 *mine = reinterpret_cast<double2 *>(cfold + (size_t) warp * fold_stride + kc * 8 + 2 * lq);
+#pragma unroll
+      for (int t = 0; t < NTILES; t++) mine[t * 32] = make_double2(C[t][0], C[t][1]);
+#pragma unroll
+      for (int i = 0; i < NT; i++)
+#pragma unroll
+        for (int h = 0; h < NH; h++) mine[(NTILES + h * NT + i) * 32] = make_double2(CH[i][h][0], CH[i][h][1]);
+    }
+    block_reduce3(hp_acc, nacc, lws, red, tid);   // contains a __syncthreads()
+    if (tid == 0) {
+      acc[a.SL.hp] = hp_acc + halfD * lws;
+      acc[a.SL.nacc] = nacc;
+    }
+    if (do_pairs)
+      for (int p = tid; p < NP; p += kBlock) {
+        int pa, pb;
+        pair_from_index(p, D, pa, pb);
+        const int i = pa >> 3, jj = pb >> 3;
+        const int t = i * NT - i * (i - 1) / 2 + (jj - i);
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) s += cfold[(size_t) w * fold_stride + t * 64 + (pa & 7) * 8 + (pb & 7)];
+        acc[a.SL.T + p] = s;
+      }
+    for (int e = tid; e < q * (D + 1); e += kBlock) {   // (cluster k, row r): r < D -> s_k[r], r == D -> n_k
+      const int k = e / (D + 1), r = e - k * (D + 1);
+      const int t = NTILES + (k >> 3) * NT + (r >> 3);
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) s += cfold[(size_t) w * fold_stride + t * 64 + (r & 7) * 8 + (k & 7)];
+      if (r < D) acc[a.SL.sk + k * D + r] = s;
+      else acc[a.SL.nk + k] = s;
+    }
+    __syncthreads();
+    double *out = a.partials + (size_t) a.seg_slot[seg] * E;
+    for (int e = tid; e < E; e += kBlock) out[e] = acc[e];
+    init_const_rows();     // the output tiles overwrote them
+    fence_proxy_async();   // generic-proxy writes to the buffers before the next segment's TMA copies
+    __syncthreads();
+  }
+}
+
+template <bool TDIST, int NH>
+int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
+  constexpr int D = BSB_D;
+  const FastSmem L = fast_smem_layout(D, a.PL.q, a.SL.E, TDIST, NH, a.maxdeg);
+  static size_t attr[64] = {};   // opted-in dynamic shared memory, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || L.bytes > attr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_fast<D, TDIST, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.bytes);
+    if (e != cudaSuccess) return (int) e;
+    if (dev >= 0 && dev < 64) attr[dev] = L.bytes;
+  }
+  k_sweep_fast<D, TDIST, NH><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
+  return 0;
+}
+
+// shared precision, q <= kFastMaxQ only (the caller checks)
+void launch_fast(int tdist, const SweepArgs &a, int grid, cudaStream_t s) {
+  const int nh = (a.PL.q + 7) / 8;
+  if (tdist) { if (nh == 1) launch_fast_t<true, 1>(a, grid, s); else launch_fast_t<true, 2>(a, grid, s); }
+  else { if (nh == 1) launch_fast_t<false, 1>(a, grid, s); else launch_fast_t<false, 2>(a, grid, s); }
+}
+
+size_t fast_smem(int tdist, const SweepArgs &a) {
+  return fast_smem_layout(BSB_D, a.PL.q, a.SL.E, tdist, (a.PL.q + 7) / 8, a.maxdeg).bytes;
+}
+
+FastRegistrar reg(BSB_D, launch_fast, fast_smem);
+
+}   // namespace
+}   // namespace bsb

@@ -150,9 +150,10 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
           if (TDIST) wj = a.w[j];
         } else {
           const uint32_t og = (uint32_t) origbuf[cur * kBlock + tid];
-          double u_prop, u_acc;
-          rng_uniform2(key, P_SPOT_U, og, it, 0u, u_prop, u_acc);
-          const int zn = propose_label(zk, q, u_prop);
+          uint32_t prop_bits;
+          double u_acc, u_sq;
+          rng_spot(key, og, it, prop_bits, u_acc, u_sq);   // one Philox block: proposal, accept, first gamma attempt
+          const int zn = propose_label_bits(zk, q, prop_bits);
           int deg = 0, cp = 0, cn = 0;
           for (int e = 0; e < a.maxdeg; e++) {
             const int32_t nb = ellbuf[(cur * a.maxdeg + e) * kBlock + tid];
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kBlock) k_sweep(const SweepArgs a) {
             const double aL = quadform<D>(y, s_PL + (VVV ? zk * NP : 0));
             const double bL = dotv<D>(y, s_gL + zk * D);
             const double quad = aL - 2.0 * bL + s_cL[zk];
-            wj = rng_gamma(key, P_SPOT_GAMMA, og, it, w_alpha, 2.0 / (quad + 4.0));
+            wj = rng_gamma_spot(key, og, it, w_alpha, 2.0 / (quad + 4.0), u_sq);
           }
           const double lin_p = s_c[zk] - 2.0 * dotv<D>(y, s_g + zk * D);
           const double lin_n = s_c[zn] - 2.0 * dotv<D>(y, s_g + zn * D);

@@ -28,6 +28,10 @@ __global__ void k_permute_center(const double *Y, int64_t src_ld, int64_t count,
                                  const double *ybar, double *Yp, int64_t dst_ld, int64_t orig_off) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  if (orig[i] < 0) {   // hole of the internal order
+    for (int c = 0; c < d; c++) Yp[(size_t) c * dst_ld + i] = 0.0;
+    return;
+  }
   const int64_t o = orig[i] - orig_off;
   for (int c = 0; c < d; c++) Yp[(size_t) c * dst_ld + i] = Y[(size_t) c * src_ld + o] - ybar[c];
 }
@@ -36,7 +40,7 @@ __global__ void k_permute_center(const double *Y, int64_t src_ld, int64_t count,
 __global__ void k_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n,
                            int32_t *z_out, double *w_out, int64_t orig_off) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || orig[i] < 0) return;
   const int64_t o = orig[i] - orig_off;
   z_out[o] = (int32_t) z[i] + 1;
   if (w_out) w_out[o] = w[i];

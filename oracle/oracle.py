@@ -98,6 +98,24 @@ def gamma(seed, purpose, index0, count, it, shape, scale):
     return o
 
 
+def spot_draw(seed, index, it):
+    """(proposal bits, u_accept, u of the first gamma attempt) of one spot and iteration: one Philox block."""
+    o = np.zeros(3)
+    lib().orc_spot_draw(C.c_uint64(seed), C.c_uint32(index), C.c_uint32(it), _p(o, C.c_double))
+    return int(o[0]), float(o[1]), float(o[2])
+
+
+def gamma_spot(seed, index, it, shape, scale):
+    """t-model weight draw of one spot (Marsaglia-Tsang on the per-spot draw layout)."""
+    f = lib().orc_gamma_spot
+    f.restype = C.c_double
+    return float(f(C.c_uint64(seed), C.c_uint32(index), C.c_uint32(it), C.c_double(shape), C.c_double(scale)))
+
+
+def propose_label_bits(z_prev, q, bits):
+    return int(lib().orc_propose_label_bits(int(z_prev), int(q), C.c_uint32(bits)))
+
+
 def dmvnrm_arma_fast(x, mean, sigma, w=None, q1_compat=True):
     """log N(x; mean, sigma[/w]) exactly as src/cluster.cpp:83-106 evaluates it."""
     x = np.atleast_2d(np.asarray(x, dtype=np.float64))

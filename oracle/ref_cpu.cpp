@@ -230,6 +230,50 @@ struct Rng {
   }
 };
 
+// ---- per-spot draws of the cluster samplers' z / w scan (mirrors bayesspace_b200/csrc/rng.cuh) ----
+// One Philox block (spot, 0, iteration, P_SPOT_U) serves the scan's three uniforms: word 0 -> proposal
+// (sample(qlessk, 1), src/cluster.cpp:278), words 1..2 -> the 53-bit uniform of the accept step (:304),
+// word 3 -> the uniform of the first Marsaglia-Tsang attempt of R::rgamma (:518).  The normal of attempt t
+// comes from block (spot, t, iteration, P_SPOT_GAMMA); attempts t >= 1 take their uniform from word 0 of
+// block (spot, 0x40000000 + t, iteration, P_SPOT_GAMMA).
+struct SpotDraw {
+  uint32_t prop_bits;
+  double u_acc, u_first;
+};
+inline double u32c(uint32_t x) { return ((double) x + 0.5) * (1.0 / 4294967296.0); }
+inline SpotDraw spot_draw(const Rng &rng, uint32_t index, uint32_t iter) {
+  uint32_t c[4] = {index, 0u, iter, P_SPOT_U}, o[4];
+  philox4x32_10(c, rng.key, o);
+  return SpotDraw{o[0], Rng::u53(o[1], o[2]), u32c(o[3])};
+}
+// sample(qlessk, 1): element floor((q-1) * bits / 2^32) of the labels 1..q without z_prev, ascending.
+inline int propose_label_bits(int z_prev, int q, uint32_t bits) {
+  const int t = (int) (((uint64_t) bits * (uint64_t) (q - 1)) >> 32);
+  return (t + 1 < z_prev) ? t + 1 : t + 2;
+}
+// R::rgamma(shape >= 1, scale) stand-in (Marsaglia-Tsang) with the draw layout above.
+inline double gamma_spot(const Rng &rng, uint32_t index, uint32_t iter, double shape, double scale, double u_first) {
+  if (!(shape >= 1.0) || !(scale > 0.0)) return std::numeric_limits<double>::quiet_NaN();
+  const double dd = shape - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * dd);
+  for (uint32_t t = 0; t < 0x3fffffffu; t++) {
+    double x, x_unused;
+    rng.normal2(P_SPOT_GAMMA, index, iter, t, x, x_unused);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = u_first;
+    if (t) {
+      uint32_t cc[4] = {index, 0x40000000u + t, iter, P_SPOT_GAMMA}, o[4];
+      philox4x32_10(cc, rng.key, o);
+      u = u32c(o[0]);
+    }
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return dd * v * scale;
+    if (std::log(u) < 0.5 * x2 + dd * (1.0 - v + std::log(v))) return dd * v * scale;
+  }
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
 // Rcpp sugar sample(x,1,TRUE,{1-p,p}): probabilities sorted descending, one
 // uniform, cumulative inversion.  Returns true when the second element ("new") is picked.
 inline bool sample_two(double p_new, double u) {
@@ -456,11 +500,11 @@ int run_cluster(const ClusterIO &io) {
           quad += (yj[a] - mu_long[(size_t) j * d + a]) * s;
         }
         const double w_beta = 2.0 / (quad + 4.0);
-        w[j] = rng.gamma(P_SPOT_GAMMA, (uint32_t) j, (uint32_t) i, w_alpha, w_beta);
+        w[j] = gamma_spot(rng, (uint32_t) j, (uint32_t) i, w_alpha, w_beta, spot_draw(rng, (uint32_t) j, (uint32_t) i).u_first);
       }
-      double u_prop, u_acc;
-      rng.uniform2(P_SPOT_U, (uint32_t) j, (uint32_t) i, 0, u_prop, u_acc);
-      const int z_new = propose_label(z_prev, q, u_prop);
+      const SpotDraw dr = spot_draw(rng, (uint32_t) j, (uint32_t) i);
+      const double u_acc = dr.u_acc;
+      const int z_new = propose_label_bits(z_prev, q, dr.prop_bits);
       const int dg = io.g.deg(j);
       const int32_t *nb = io.g.nb(j);
       double h_prev = 0.0, h_new = 0.0;
@@ -845,6 +889,17 @@ void orc_normal(uint64_t seed, uint32_t purpose, uint32_t index, uint32_t iter, 
   Rng r(seed);
   for (int m = 0; m < count; m++) out[m] = r.normal(purpose, index, iter, m0 + (uint32_t) m);
 }
+// (prop_bits, u_acc, u_first) of one spot and iteration; out[0] holds prop_bits as a double
+void orc_spot_draw(uint64_t seed, uint32_t index, uint32_t iter, double *out) {
+  const SpotDraw d = spot_draw(Rng(seed), index, iter);
+  out[0] = (double) d.prop_bits; out[1] = d.u_acc; out[2] = d.u_first;
+}
+double orc_gamma_spot(uint64_t seed, uint32_t index, uint32_t iter, double shape, double scale) {
+  const Rng rng(seed);
+  return gamma_spot(rng, index, iter, shape, scale, spot_draw(rng, index, iter).u_first);
+}
+int orc_propose_label_bits(int z_prev, int q, uint32_t bits) { return propose_label_bits(z_prev, q, bits); }
+
 void orc_gamma(uint64_t seed, uint32_t purpose, uint32_t index0, int count, uint32_t iter,
                double shape, double scale, double *out) {
   Rng r(seed);

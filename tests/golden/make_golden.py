@@ -33,7 +33,7 @@ def main():
         order = np.lexsort((np.arange(w.n), lattice_colour(w))).astype(np.int32)
         for sampler in ("iterate", "iterate_vvv", "iterate_t", "iterate_t_vvv"):
             key = "%s_%s" % (workload, sampler)
-            case = dict(key=key, workload=workload, sampler=sampler, nrep=25, thin=5, seed=20261019)
+            case = dict(key=key, workload=workload, sampler=sampler, nrep=25, thin=5, seed=20261020)
             out = getattr(O, sampler)(w.Y, g, case["nrep"], case["thin"], w.n, w.d, w.gamma, w.q, w.init, w.mu0,
                                       w.lambda0, w.alpha, w.beta, seed=case["seed"], order=order)
             arrays[key + "_order"] = order

@@ -58,6 +58,12 @@ def sample_without(q, z_prev, u):
     return rest[min(int(np.floor(len(rest) * u)), len(rest) - 1)]
 
 
+def sample_without_bits(q, z_prev, bits):
+    """The same with the uniform given as 32 random bits: u = bits / 2^32, in exact integer arithmetic."""
+    rest = [k for k in range(1, q + 1) if k != z_prev]
+    return rest[(int(bits) * len(rest)) >> 32]
+
+
 def sample_two(z_prev, z_new, p, u):
     """sample({z_prev, z_new}, 1, TRUE, {1 - p, p}): Rcpp sugar sorts the probabilities in DECREASING order and
     inverts the cumulative sum with one uniform."""
@@ -120,9 +126,9 @@ def run(O, variant, Y, nbrs, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alp
             if tdist:
                 r = Y[j] - mu_long[j]
                 w_beta = 2.0 / (r @ lam[kp] @ r + 4.0)
-                w[j] = O.gamma(seed, P_SPOT_GAMMA, j, 1, i, w_alpha, w_beta)[0]
-            u_prop, u_acc = O.uniform2(seed, P_SPOT_U, j, i, 0)
-            z_new = sample_without(q, z_prev, u_prop)
+                w[j] = O.gamma_spot(seed, j, i, w_alpha, w_beta)
+            prop_bits, u_acc, _ = O.spot_draw(seed, j, i)
+            z_new = sample_without_bits(q, z_prev, prop_bits)
             kn = z_new - 1 if vvv else 0
             scale = w[j] if tdist else 1.0
             h_prev = dmvnrm_arma_fast(Y[j].copy(), mu[z_prev - 1], sig[kp] / scale)

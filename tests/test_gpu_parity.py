@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SEED = 20261019
+SEED = 20261020
 
 
 def _setup(bsb, name, **kw):
@@ -130,8 +130,9 @@ def test_mh_ratio_probe(bsb, oracle, fname, model, precision, name):
     assert np.array_equal(st["z"], ref["z"][4])
     wts = dry["w"] if model == "t" else None
     hp, hn = oracle.h_values(fname, w.Y, csr, st["z"], wts, mu4, sig4, w.gamma, dry["z_new"])
-    assert np.max(np.abs(dry["h_prev"] - hp) / np.abs(hp)) < 1e-9
-    assert np.max(np.abs(dry["h_new"] - hn) / np.abs(hn)) < 1e-9
+    # relative to the size of the terms (Potts + log-density, both O(1..100)): h itself crosses zero
+    assert np.max(np.abs(dry["h_prev"] - hp) / np.maximum(np.abs(hp), 1.0)) < 1e-9
+    assert np.max(np.abs(dry["h_new"] - hn) / np.maximum(np.abs(hn), 1.0)) < 1e-9
     pr = np.minimum(1.0, np.exp(hn - hp))
     assert np.max(np.abs(dry["prob"] - pr)) < 1e-9
     ch.close()
