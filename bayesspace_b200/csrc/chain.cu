@@ -180,22 +180,23 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
 }
 
 int choose_groups(int64_t n) { return n >= 262144 ? kGroups : 1; }
-int choose_segment(int64_t n, int ncol) {
-  // Tiles per segment (= per CTA of a sweep launch): a function of the GLOBAL problem only (n, colours), never of
+int choose_segment(int64_t n, int ncol, int d) {
+  // Tiles per segment (= per CTA of a sweep launch): a function of the GLOBAL problem only (n, colours, d), never of
   // the GPU count, because the fold order -- hence the bits of a chain -- depends on it.
   int64_t tps = n / ((int64_t) kBlock * 2048);
   tps = std::max<int64_t>(1, std::min<int64_t>(8, tps));
   if (choose_groups(n) == kGroups && ncol > 0) {
-    // Sharded sizes: a colour phase of W ranks launches (kGroups / W) * ceil(tiles / t) CTAs onto 148 SMs x 4 resident
-    // CTAs; its time is about waves * t.  Pick the t whose wave quantisation loss, summed over W = 1, 2, 4, 8, is
-    // smallest (at 10M spots: t = 9 -> 8 / 4 / 2 / 1 full waves instead of 9 / 5 / 3 / 2 with t = 8).
-    const int64_t slots = 148 * 4;
+    // Sharded sizes: a colour phase of W ranks launches (kGroups / W) * ceil(tiles / t) CTAs onto 148 SMs x (resident
+    // CTAs of k_sweep_fast<d>); its time is about waves * (t + fixed cost of a CTA, ~half a tile).  Pick the t whose
+    // cost, summed over W = 1, 2, 4, 8, is smallest (10M spots, d = 15: t = 9 -> 8 / 4 / 2 / 1 full waves).
+    const int64_t slots = 148 * (d <= 16 ? 4 : (d <= 24 ? 3 : 2));
     const int64_t tiles = ((n / kGroups + ncol - 1) / ncol + kBlock - 1) / kBlock;   // per (shard, colour)
-    int64_t best = 0, best_cost = 0;
-    for (int64_t t = 6; t <= 12; t++) {
+    int64_t best = 0;
+    double best_cost = 0;
+    for (int64_t t = 2; t <= 12; t++) {
       const int64_t segs = (tiles + t - 1) / t;
-      int64_t cost = 0;
-      for (int W = 1; W <= 8; W *= 2) cost += ((kGroups / W * segs + slots - 1) / slots) * t * W;
+      double cost = 0;
+      for (int W = 1; W <= 8; W *= 2) cost += (double) ((kGroups / W * segs + slots - 1) / slots) * ((double) t + 0.5) * W;
       if (best == 0 || cost < best_cost) { best = t; best_cost = cost; }
     }
     tps = best;
@@ -452,7 +453,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if (rc) return rc;
   }
   mark("colouring");
-  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol), plan.g0, plan.g1, plan.lo, plan.hi, kOrderAlign);
+  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol, d), plan.g0, plan.g1, plan.lo, plan.hi, kOrderAlign);
   const SpotOrder &ord = ch->ord;
   const int64_t n_pos = ch->n_pos = ord.npos;   // ghosts follow the own positions
   ch->ld = (n_pos + (int64_t) plan.ghosts.size() + 31) / 32 * 32;

@@ -53,7 +53,7 @@ struct SpotOrder {
 int select_device(int device);
 constexpr int kOrderAlign = 32;   // alignment of the ranges in the cluster samplers' internal order
 int choose_groups(int64_t n);
-int choose_segment(int64_t n, int ncol = 0);   // ncol = 0: the plain n-based rule (probes, deconvolution)
+int choose_segment(int64_t n, int ncol = 0, int d = 15);   // ncol = 0: the plain n-based rule (probes, deconvolution)
 void param_kernel_init();
 
 }   // namespace bsb

@@ -22,6 +22,8 @@
 // This kernel is pure latency (d <= 32): every d x d operation is spread over the whole CTA and over ALL
 // matrices of a phase at once (the q posterior precisions of the mu step; the q Wishart draws of the VVV
 // samplers), one thread per matrix element, so the critical path is d steps of one FMA + a barrier.
+#include <cstdlib>
+
 #include "chain.hpp"
 #include "rng.cuh"
 
@@ -147,7 +149,7 @@ __device__ __forceinline__ void warp_inv_upper_reg(const double *U, double *T, i
     if (lane < D) T[lane * D + i] = i <= lane ? t[i] : 0.0;
 }
 
-// D = exact dimension 1..16 (register path) or 0 (run-time d up to 32, shared-memory path)
+// D = exact dimension 1..32 (register path) or 0 (run-time d up to 32, shared-memory path)
 template <int D>
 __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, int batch) {
   extern __shared__ double sm[];
@@ -410,9 +412,11 @@ static const size_t kParamSmemMax = 220 * 1024;
 
 typedef void (*param_kernel_t)(ParamArgs, int, int);
 static param_kernel_t *param_kernel_table() {
-  static param_kernel_t t[17] = {k_param<0>,  k_param<1>,  k_param<2>,  k_param<3>,  k_param<4>,  k_param<5>,
-                                 k_param<6>,  k_param<7>,  k_param<8>,  k_param<9>,  k_param<10>, k_param<11>,
-                                 k_param<12>, k_param<13>, k_param<14>, k_param<15>, k_param<16>};
+  static param_kernel_t t[kMaxD + 1] = {
+      k_param<0>,  k_param<1>,  k_param<2>,  k_param<3>,  k_param<4>,  k_param<5>,  k_param<6>,  k_param<7>,  k_param<8>,
+      k_param<9>,  k_param<10>, k_param<11>, k_param<12>, k_param<13>, k_param<14>, k_param<15>, k_param<16>, k_param<17>,
+      k_param<18>, k_param<19>, k_param<20>, k_param<21>, k_param<22>, k_param<23>, k_param<24>, k_param<25>, k_param<26>,
+      k_param<27>, k_param<28>, k_param<29>, k_param<30>, k_param<31>, k_param<32>};
   return t;
 }
 
@@ -426,9 +430,10 @@ void launch_param(const ParamArgs &a, cudaStream_t stream) {
   int batch = (int) std::min<size_t>((size_t) want, avail / per_mat);
   if (batch < 1) batch = 1;
   const size_t smem = base + (stats_in_smem ? stats_bytes : 0) + (size_t) batch * per_mat;
-  // d <= 16: factorisations with one register-resident column per lane (kernel instantiated for the exact d);
-  // larger d: shared-memory versions with run-time d
-  param_kernel_table()[d <= 16 ? d : 0]<<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
+  // factorisations with one register-resident column per lane, kernel instantiated for the exact d (k_param<0>,
+  // the shared-memory version with run-time d, stays as the reference implementation: BSB200_PARAM_GENERIC=1)
+  static const bool generic = std::getenv("BSB200_PARAM_GENERIC") != nullptr;
+  param_kernel_table()[generic ? 0 : d]<<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
 }
 
 #ifdef BSB_PARAM_TIMING
@@ -438,7 +443,7 @@ extern "C" int bsb200_debug_param_timing(long long *out16) {
 #endif
 
 void param_kernel_init() {
-  for (int i = 0; i <= 16; i++)
+  for (int i = 0; i <= kMaxD; i++)
     cudaFuncSetAttribute(param_kernel_table()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kParamSmemMax);
 }
 

@@ -145,38 +145,96 @@ __device__ __forceinline__ int propose_label_bits(int z_prev, int q, uint32_t bi
 // Accept step of sample({z, z'}, 1, TRUE, {1 - p, p}) with p = min(1, exp(delta)), decided in the log domain:
 // with v = u (p >= 1/2) or 1 - u (p < 1/2) the rule of sample_two() reads log v <= delta resp. log v < delta.
 // A single-precision logarithm decides whenever its error bound cannot change the answer; the (rare) ambiguous
-// cases evaluate exp(delta) and sample_two() exactly as the reference's arithmetic does.
+// cases evaluate exp(delta) and sample_two() exactly as the reference's arithmetic does.  Branch-free up to that
+// fallback, so the caller's surrounding code stays one basic block.
 __device__ __forceinline__ bool mh_accept(double delta, double u) {
-  if (delta >= 0.0) return true;
   const double v = (delta >= -0.69314718055994530942) ? u : 1.0 - u;
   const float lf = __logf((float) v);
   const double gap = delta - (double) lf;
-  if (fabs(gap) > 1e-4 * (1.0 + fabs((double) lf))) return gap > 0.0;
-  return sample_two(exp(delta), u);
+  const bool decisive = fabs(gap) > 1e-4 * (1.0 + fabs((double) lf));
+  bool acc = (delta >= 0.0) | (decisive & (gap > 0.0));
+  if (!decisive && delta < 0.0) acc = sample_two(exp(delta), u);
+  return acc;
 }
 
-// Gamma(shape >= 1, scale) for the t-model weights (Marsaglia & Tsang), draws laid out as described above.
-// The second acceptance test, log u < x^2/2 + d (1 - v + log v), is screened in single precision the same way.
+// ---- natural logarithm of a positive normal double from a 128-entry table (in shared memory) ------------------
+// m = mantissa scaled to [0.75, 1.5), c = centre of the 2^-8-wide bin of m (exactly representable: the leading bits
+// of m), log m = log c + log1p((m - c) / c) with a degree-7 polynomial (|(m-c)/c| < 2^-7.9).  About 25 instructions
+// without a branch, against ~60 with special-case branches for log(); accurate to ~1e-16 relative (the oracle uses
+// libm's log; the t-model weights are compared at 1e-9).  tab[i] = {1 / c_i, log c_i}.
+__device__ __forceinline__ void log_table_entry(int i, double2 &e) {
+  const int chi = 0x3fe80000 + (i << 13) + 0x1000;   // high word of the bin centre
+  const double c = __hiloint2double(chi, 0);
+  e.x = 1.0 / c;
+  e.y = log(c);
+}
+__device__ __forceinline__ double log_tab(double u, const double2 *__restrict__ tab) {
+  const int hi = __double2hiint(u), lo = __double2loint(u);
+  int e = (hi >> 20) - 1023;
+  int mh = (hi & 0x000fffff) | 0x3ff00000;
+  const bool up = mh >= 0x3ff80000;   // m >= 1.5: halve it
+  mh = up ? mh - 0x00100000 : mh;
+  e += up ? 1 : 0;
+  const double m = __hiloint2double(mh, lo);
+  const double c = __hiloint2double((mh & 0xffffe000) | 0x1000, 0);
+  const double2 t = tab[(mh - 0x3fe80000) >> 13];
+  const double r = (m - c) * t.x;
+  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(p, r, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double l1p = fma(p, r * r, r);
+  const double ef = (double) e;
+  return fma(ef, 0.693147180369123816490, t.y) + fma(ef, 1.90821492927058770002e-10, l1p);
+}
+
+// First Box-Muller output from one Philox block, logarithm from the table.
+__device__ __forceinline__ double normal_from_block(uint4 o, const double2 *__restrict__ tab) {
+  const double u0 = u53(o.x, o.y), u1 = u53(o.z, o.w);
+  return sqrt(-2.0 * log_tab(u0, tab)) * cospi(2.0 * u1);
+}
+
+// One Marsaglia-Tsang attempt for Gamma(shape >= 1): true when (x, u) is accepted, v3 = (1 + c x)^3.
+// The second test, log u < x^2/2 + dd (1 - v3 + log v3), is screened in single precision like mh_accept().
+__device__ __forceinline__ bool mt_attempt(double x, double u, double dd, double c, double &v3) {
+  const double v = 1.0 + c * x;
+  v3 = v * v * v;
+  const double x2 = x * x;
+  const bool squeeze = u < 1.0 - 0.0331 * x2 * x2;
+  const float lu = __logf((float) u), lv = __logf((float) v3);
+  const double gap = (0.5 * x2 + dd * ((1.0 - v3) + (double) lv)) - (double) lu;
+  const bool decisive = fabs(gap) > 1e-4 * (1.0 + fabs((double) lu) + dd * (1.0 + fabs((double) lv)));
+  bool ok = (v > 0.0) & (squeeze | (decisive & (gap > 0.0)));
+  if (v > 0.0 && !squeeze && !decisive) ok = log(u) < 0.5 * x2 + dd * (1.0 - v3 + log(v3));
+  return ok;
+}
+
+// Gamma(shape >= 1, scale) for the t-model weights (Marsaglia & Tsang), draws laid out as described above:
+// x0 / u_first belong to attempt 0; later attempts (about 1 in 200 spots at shape 9) draw their own.
+__device__ __forceinline__ double rng_gamma_spot(Key key, uint32_t index, uint32_t iter, double shape, double scale,
+                                                 double x0, double u_first, const double2 *__restrict__ tab) {
+  const double dd = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+  double x = x0, u = u_first, v3;
+  uint32_t t = 0;
+  while (!mt_attempt(x, u, dd, c, v3)) {
+    if (++t >= 0x3fffffffu) return __longlong_as_double(0x7ff8000000000000ll);
+    x = normal_from_block(philox4x32_10(index, t, iter, P_SPOT_GAMMA, key), tab);
+    u = u32c(philox4x32_10(index, 0x40000000u + t, iter, P_SPOT_GAMMA, key).x);
+  }
+  return dd * v3 * scale;
+}
+
+// The same draw without the table (k_sweep, sweep_kernels.cu): libm-style log() in the Box-Muller transform.
 __device__ __forceinline__ double rng_gamma_spot(Key key, uint32_t index, uint32_t iter, double shape, double scale,
                                                  double u_first) {
   if (!(shape >= 1.0) || !(scale > 0.0)) return __longlong_as_double(0x7ff8000000000000ll);
   const double dd = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+  double u = u_first, v3;
   for (uint32_t t = 0; t < 0x3fffffffu; t++) {
     const double x = rng_normal_first(key, P_SPOT_GAMMA, index, iter, t);
-    double v = 1.0 + c * x;
-    if (v <= 0.0) continue;
-    v = v * v * v;
-    double u = u_first;
     if (t) u = u32c(philox4x32_10(index, 0x40000000u + t, iter, P_SPOT_GAMMA, key).x);
-    const double x2 = x * x;
-    bool ok = u < 1.0 - 0.0331 * x2 * x2;
-    if (!ok) {
-      const float lu = __logf((float) u), lv = __logf((float) v);
-      const double gap = (0.5 * x2 + dd * ((1.0 - v) + (double) lv)) - (double) lu;
-      if (fabs(gap) > 1e-4 * (1.0 + fabs((double) lu) + dd * (1.0 + fabs((double) lv)))) ok = gap > 0.0;
-      else ok = log(u) < 0.5 * x2 + dd * (1.0 - v + log(v));
-    }
-    if (ok) return dd * v * scale;
+    if (mt_attempt(x, u, dd, c, v3)) return dd * v3 * scale;
   }
   return __longlong_as_double(0x7ff8000000000000ll);
 }

@@ -40,20 +40,21 @@ constexpr int kRowB = 128;   // bytes of one row of a Y box (16 spots) and of an
 // Shared-memory carve-up (byte offsets; the per-warp areas start at a 1024-byte boundary, which SWIZZLE_128B needs
 // for its pattern to be a function of the row index alone).
 struct FastSmem {
-  int g, c, gL, cL, PL, pot, acc, red, mbar, shared_bytes, warp_stride, ybox, ell, orig, wst, zst;
+  int g, c, gL, cL, PL, pot, logtab, acc, red, mbar, shared_bytes, warp_stride, ybox, ell, orig, wst, zst;
   size_t bytes;
 };
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline FastSmem fast_smem_layout(int D, int q, int E, bool tdist, int nh, int maxdeg) {
   FastSmem s;
-  const int DS = D + (D & 1), NP = D * (D + 1) / 2, DP = (D + 1 + 7) / 8 * 8;
+  const int RS = D + (D & 1) + 2, NP = D * (D + 1) / 2, DP = (D + 1 + 7) / 8 * 8;   // RS: row stride of g / gL
   int o = 0;
-  s.g = o; o += q * DS * 8;
-  s.gL = o; o += tdist ? q * DS * 8 : 0;
+  s.g = o; o += q * RS * 8;
+  s.gL = o; o += tdist ? q * RS * 8 : 0;
   s.PL = o; o += tdist ? align16(NP * 8) : 0;
   s.c = o; o += align16(q * 8);
   s.cL = o; o += tdist ? align16(q * 8) : 0;
   s.pot = o; o += align16((kMaxDeg + 1) * 8);
+  s.logtab = o; o += tdist ? 128 * 16 : 0;
   s.acc = o; o += align16(E * 8);
   s.red = o; o += align16(3 * kWarps * 8);
   s.mbar = o; o += kWarps * 2 * 8;
@@ -118,42 +119,13 @@ __device__ __forceinline__ double dot2(const double (&y)[D], const double *__res
   return s0 + s1;
 }
 
-// Potts counts over the neighbour ids of this lane's spot (rows of 32 ids, -1 = padding).
-template <int NB>
-__device__ __forceinline__ void potts_counts(const int32_t *__restrict__ ellrow, int nb_rows, const uint8_t *__restrict__ z,
-                                             int zk, int zn, int &deg, int &cp, int &cn) {
-  deg = cp = cn = 0;
-  if (NB > 0) {
-    int32_t nb[NB > 0 ? NB : 1];
-    int zu[NB > 0 ? NB : 1];
-#pragma unroll
-    for (int e = 0; e < NB; e++) nb[e] = e < nb_rows ? ellrow[e * 32] : -1;
-#pragma unroll
-    for (int e = 0; e < NB; e++) zu[e] = nb[e] >= 0 ? (int) z[nb[e]] : -1;
-#pragma unroll
-    for (int e = 0; e < NB; e++) {
-      deg += nb[e] >= 0;
-      cp += zu[e] == zk;
-      cn += zu[e] == zn;
-    }
-  } else {
-    for (int e = 0; e < nb_rows; e++) {
-      const int32_t nb = ellrow[e * 32];
-      if (nb >= 0) {
-        const int zu = z[nb];
-        deg++;
-        cp += zu == zk;
-        cn += zu == zn;
-      }
-    }
-  }
-}
+constexpr int kNbInline = 6;   // neighbour slots handled in the straight-line part (hex lattice degree); the rest in a loop
 
 template <int D, bool TDIST, int NH>
 __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     k_sweep_fast(const __grid_constant__ SweepArgs a, const __grid_constant__ SweepMaps maps) {
   extern __shared__ __align__(1024) unsigned char smdyn[];
-  constexpr int NP = D * (D + 1) / 2, DS = D + (D & 1);
+  constexpr int NP = D * (D + 1) / 2, RS = D + (D & 1) + 2;   // RS = 2 (mod 16) doubles: rows of different clusters start in different banks
   constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, DP = TileGeom<D>::DP;
   constexpr int YBOX = DP * kRowB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -163,6 +135,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   double *s_g = reinterpret_cast<double *>(smraw + L.g), *s_c = reinterpret_cast<double *>(smraw + L.c);
   double *s_gL = reinterpret_cast<double *>(smraw + L.gL), *s_cL = reinterpret_cast<double *>(smraw + L.cL);
   double *s_PL = reinterpret_cast<double *>(smraw + L.PL), *s_pot = reinterpret_cast<double *>(smraw + L.pot);
+  double2 *s_logtab = reinterpret_cast<double2 *>(smraw + L.logtab);
   double *acc = reinterpret_cast<double *>(smraw + L.acc), *red = reinterpret_cast<double *>(smraw + L.red);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smraw + L.mbar) + 2 * warp;
   unsigned char *wbase = smraw + L.shared_bytes + (size_t) warp * L.warp_stride;
@@ -177,8 +150,8 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   if (*a.err) return;
   if (!stats_only) {
     const double *Pm = a.params;
-    for (int e = tid; e < q * DS; e += kBlock) {
-      const int k = e / DS, cc = e - k * DS;
+    for (int e = tid; e < q * RS; e += kBlock) {
+      const int k = e / RS, cc = e - k * RS;
       s_g[e] = cc < D ? Pm[a.PL.g + k * D + cc] : 0.0;
       if (TDIST) s_gL[e] = cc < D ? Pm[a.PL.gL + k * D + cc] : 0.0;
     }
@@ -189,6 +162,8 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     if (TDIST)
       for (int e = tid; e < NP + (NP & 1); e += kBlock) s_PL[e] = e < NP ? Pm[a.PL.PL + e] : 0.0;
     for (int e = tid; e <= kMaxDeg; e += kBlock) s_pot[e] = e ? a.gamma / e * 2 : 0.0;   // (gamma / |N_j|) * 2 as at :289
+    if (TDIST)
+      for (int e = tid; e < 128; e += kBlock) log_table_entry(e, s_logtab[e]);
   }
   // constant rows of the four boxes: row D = 1 (its products give n_k and the sum of weights), rows beyond = 0
   auto init_const_rows = [&]() {
@@ -253,51 +228,75 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       const int64_t j = (int64_t) begin + 32 * sub + lane;
       const bool active = 32 * sub + lane < count;
       const unsigned char *ycur = ybuf + 2 * cur * YBOX;
-      uint8_t zk8 = 255;
-      if (active) zk8 = a.z[j];
+      // Every lane runs the straight-line code below; lanes beyond the segment's end sit on holes of the internal
+      // order (zero PCs, no neighbours) and are masked out of every store and statistic.
+      const int zk = a.z[j];
       mbar_wait(mbar + cur, (ntile >> 1) & 1);
 
       double wj = active ? 1.0 : 0.0;
-      int zfinal = zk8;
-      if (active) {
-        const int zk = zk8;
-        if (stats_only) {
-          if (TDIST) wj = a.w[j];
-        } else {
-          const uint32_t og = (uint32_t) worig[cur * 32 + lane];
-          uint32_t prop_bits;
-          double u_acc, u_sq;
-          rng_spot(key, og, it, prop_bits, u_acc, u_sq);
-          const int zn = propose_label_bits(zk, q, prop_bits);
-          int deg, cp, cn;
+      int zfinal = active ? zk : 255;
+      if (stats_only) {
+        if (TDIST && active) wj = a.w[j];
+      } else {
+        const uint32_t og = (uint32_t) worig[cur * 32 + lane];
+        // neighbour labels: issue the gathers first, they are the longest latency of the spot
+        int zu[kNbInline];
+        {
           const int32_t *ellrow = well + cur * ell_rows * 32 + lane;
-          if (ell_rows <= 4) potts_counts<4>(ellrow, ell_rows, a.z, zk, zn, deg, cp, cn);
-          else if (ell_rows <= 6) potts_counts<6>(ellrow, ell_rows, a.z, zk, zn, deg, cp, cn);
-          else potts_counts<0>(ellrow, ell_rows, a.z, zk, zn, deg, cp, cn);
-          const double ps = s_pot[deg];
-          const double pot_p = ps * cp, pot_n = ps * cn;
-          double y[D];
-          {
-            const unsigned char *yb = ycur + my_half + my_lo;
 #pragma unroll
-            for (int c = 0; c < D; c++)
-              y[c] = *reinterpret_cast<const double *>(yb + c * kRowB + (my_chunk ^ ((c & 7) << 4)));
+          for (int e = 0; e < kNbInline; e++) {
+            const int32_t nb = e < ell_rows ? ellrow[e * 32] : -1;
+            zu[e] = nb >= 0 ? (int) a.z[nb] : -1;
           }
-          if (TDIST) {
-            // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518)
-            const double aL = quadform2<D>(y, s_PL);
-            const double bL = dot2<D>(y, s_gL + zk * DS);
-            const double quad = aL - 2.0 * bL + s_cL[zk];
-            wj = rng_gamma_spot(key, og, it, w_alpha, 2.0 / (quad + 4.0), u_sq);
+        }
+        // randomness: depends on nothing but (spot, iteration)
+        const uint4 oa = philox4x32_10(og, 0u, it, P_SPOT_U, key);
+        const double u_acc = u53(oa.y, oa.z), u_sq = u32c(oa.w);
+        double x0 = 0.0;
+        if (TDIST) x0 = normal_from_block(philox4x32_10(og, 0u, it, P_SPOT_GAMMA, key), s_logtab);
+        const int zn = propose_label_bits(zk, q, oa.x);
+        double y[D];
+        {
+          const unsigned char *yb = ycur + my_half + my_lo;
+#pragma unroll
+          for (int c = 0; c < D; c++)
+            y[c] = *reinterpret_cast<const double *>(yb + c * kRowB + (my_chunk ^ ((c & 7) << 4)));
+        }
+        double scale = 0.0;
+        if (TDIST) {
+          // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518)
+          const double aL = quadform2<D>(y, s_PL);
+          const double bL = dot2<D>(y, s_gL + zk * RS);
+          scale = 2.0 / ((aL - 2.0 * bL + s_cL[zk]) + 4.0);
+        }
+        const double lin_p = s_c[zk] - 2.0 * dot2<D>(y, s_g + zk * RS);
+        const double lin_n = s_c[zn] - 2.0 * dot2<D>(y, s_g + zn * RS);
+        int deg = 0, cp = 0, cn = 0;
+#pragma unroll
+        for (int e = 0; e < kNbInline; e++) {
+          deg += zu[e] >= 0;
+          cp += zu[e] == zk;
+          cn += zu[e] == zn;
+        }
+        for (int e = kNbInline; e < ell_rows; e++) {   // general graphs with more than 6 neighbours
+          const int32_t nb = well[(cur * ell_rows + e) * 32 + lane];
+          if (nb >= 0) {
+            const int z2 = a.z[nb];
+            deg++;
+            cp += z2 == zk;
+            cn += z2 == zn;
           }
-          const double lin_p = s_c[zk] - 2.0 * dot2<D>(y, s_g + zk * DS);
-          const double lin_n = s_c[zn] - 2.0 * dot2<D>(y, s_g + zn * DS);
-          // y^T M y and (d/2) log w_j are common to both labels: they only enter plogLik (statistics, lw)
-          const double delta = (pot_n - pot_p) - 0.5 * wj * (lin_n - lin_p);
-          const double hp_part = pot_p - 0.5 * wj * lin_p;
-          if (delta != delta) atomicExch(a.err, BSB_DEVERR_NUMERIC);   // NA probability (Rcpp sample() stops)
-          const bool accept = mh_accept(delta, u_acc);
-          if (dry) {
+        }
+        const double ps = s_pot[deg];
+        const double pot_p = ps * cp, pot_n = ps * cn;
+        if (TDIST) wj = rng_gamma_spot(key, og, it, w_alpha, scale, x0, u_sq, s_logtab);
+        // y^T M y and (d/2) log w_j are common to both labels: they only enter plogLik (statistics, lw)
+        const double delta = (pot_n - pot_p) - 0.5 * wj * (lin_n - lin_p);
+        const double hp_part = pot_p - 0.5 * wj * lin_p;
+        const bool accept = mh_accept(delta, u_acc);
+        if (active && delta != delta) atomicExch(a.err, BSB_DEVERR_NUMERIC);   // NA probability (Rcpp sample() stops)
+        if (dry) {
+          if (active) {
             const double LOG2PI = 1.8378770664093454835606594728112;
             const double logw = TDIST ? log(wj) : 0.0;
             const double aM = quadform<D>(y, a.params + a.PL.PM), ld = a.params[a.PL.logdet];
@@ -309,26 +308,28 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
             a.dry_hn[og] = pot_n + ((ld - halfD * LOG2PI) + halfD * logw - 0.5 * wj * (aM + lin_n));
             a.dry_prob[og] = prob;
             a.dry_acc[og] = accept ? 1 : 0;
-          } else {
-            if (accept) {
-              a.z[j] = (uint8_t) zn;
-              zfinal = zn;
-              nacc += 1.0;
-            }
-            if (TDIST) {
-              a.w[j] = wj;
-              // sum_j log w_j as a running product, renormalised only when it leaves [1e-150, 1e150]
-              double m2 = lw_m * wj;
-              if (!(m2 >= 1e-150 && m2 <= 1e150)) {
-                int e1, e2;
-                const double f1 = frexp(lw_m, &e1), f2 = frexp(wj, &e2);
-                m2 = f1 * f2;
-                lw_e += e1 + e2;
-              }
-              lw_m = m2;
-            }
-            hp_acc += hp_part;
           }
+        } else if (active) {
+          if (accept) {
+            a.z[j] = (uint8_t) zn;
+            zfinal = zn;
+            nacc += 1.0;
+          }
+          if (TDIST) {
+            a.w[j] = wj;
+            // sum_j log w_j as a running product, renormalised only when it leaves [1e-150, 1e150]
+            double m2 = lw_m * wj;
+            if (!(m2 >= 1e-150 && m2 <= 1e150)) {
+              int e1, e2;
+              const double f1 = frexp(lw_m, &e1), f2 = frexp(wj, &e2);
+              m2 = f1 * f2;
+              lw_e += e1 + e2;
+            }
+            lw_m = m2;
+          }
+          hp_acc += hp_part;
+        } else {
+          wj = 0.0;
         }
       }
       if (!dry) {
