@@ -21,6 +21,8 @@
 //    second Marsaglia-Tsang test decided by a single-precision screen with an exact FP64 fallback (rng.cuh);
 //  * parameters are read from shared memory as 16-byte broadcasts; the Potts scale 2 gamma / |N_j| is a table;
 //    the neighbour loop is unrolled for the lattice degrees (4 and 6).
+#include <type_traits>
+
 #include "kernels.hpp"
 #include "pipeline.cuh"
 #include "rng.cuh"
@@ -40,7 +42,7 @@ constexpr int kRowB = 128;   // bytes of one row of a Y box (16 spots) and of an
 // Shared-memory carve-up (byte offsets; the per-warp areas start at a 1024-byte boundary, which SWIZZLE_128B needs
 // for its pattern to be a function of the row index alone).
 struct FastSmem {
-  int g, c, gL, cL, PL, pot, logtab, acc, red, mbar, shared_bytes, warp_stride, ybox, ell, orig, wst, zst;
+  int g, c, gL, cL, PL, pot, logtab, acc, red, mbar, shared_bytes, warp_stride, ybox, ell, orig, wst, zst, skacc;
   size_t bytes;
 };
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -66,6 +68,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(int D, int q, int E, bool t
   s.orig = w; w += 2 * kRowB;
   s.wst = w; w += 32 * 8;
   s.zst = w; w += 32;
+  s.skacc = w; w += q * DP * 8;   // per-cluster sums of the label-uniform sub-tiles (rows 0..d-1: s_k, row d: n_k)
   s.warp_stride = (w + 1023) & ~1023;
   s.bytes = (size_t) s.shared_bytes + (size_t) kWarps * s.warp_stride + 1024;   // + slack to align the base
   return s;
@@ -80,9 +83,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 
 constexpr int fast_min_blocks(int D) { return D <= 16 ? 4 : (D <= 24 ? 3 : 2); }
 
-// x^T P x with P = packed upper triangle (row-major, off-diagonals doubled), read as 16-byte broadcasts.
+// x^T P x with P = packed upper triangle, COLUMN by column (b outer, a <= b inner, off-diagonals doubled), read as
+// 16-byte broadcasts.  Consecutive FMAs of a column go to different accumulators s[a], so the FP64 latency of one
+// is covered by the others (the row-wise order is a serial chain of d FMAs per row).
 template <int D>
-__device__ __forceinline__ double quadform2(const double (&y)[D], const double *__restrict__ P) {
+__device__ __forceinline__ double quadform_cols(const double (&y)[D], const double *__restrict__ P) {
   constexpr int NP = D * (D + 1) / 2;
   const double2 *P2 = reinterpret_cast<const double2 *>(P);
   double s[D];
@@ -93,30 +98,45 @@ __device__ __forceinline__ double quadform2(const double (&y)[D], const double *
   for (int p2 = 0; p2 < (NP + 1) / 2; p2++) {
     const double2 v = P2[p2];
     s[a] = fma(v.x, y[b], s[a]);
-    if (++b == D) { a++; b = a; }
+    if (++a > b) { b++; a = 0; }
     if (2 * p2 + 1 < NP) {
       s[a] = fma(v.y, y[b], s[a]);
-      if (++b == D) { a++; b = a; }
+      if (++a > b) { b++; a = 0; }
     }
   }
-  double acc = 0.0;
+  double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-  for (int r = 0; r < D; r++) acc = fma(y[r], s[r], acc);
-  return acc;
+  for (int r = 0; r < D; r += 2) {
+    acc0 = fma(y[r], s[r], acc0);
+    if (r + 1 < D) acc1 = fma(y[r + 1], s[r + 1], acc1);
+  }
+  return acc0 + acc1;
 }
+__host__ __device__ inline int colpacked_index(int a, int b) { return b * (b + 1) / 2 + a; }   // a <= b
 
-// y . g with g padded to an even length and 16-byte aligned
-template <int D>
-__device__ __forceinline__ double dot2(const double (&y)[D], const double *__restrict__ g) {
-  const double2 *g2 = reinterpret_cast<const double2 *>(g);
-  double s0 = 0.0, s1 = 0.0;
+// Three dot products of y at once (rows padded to an even length, 16-byte aligned): six independent FMA chains.
+template <int D, bool WITH_L>
+__device__ __forceinline__ void dot3(const double (&y)[D], const double *__restrict__ gl, const double *__restrict__ gp,
+                                     const double *__restrict__ gn, double &dl, double &dp, double &dn) {
+  const double2 *l2 = reinterpret_cast<const double2 *>(gl), *p2 = reinterpret_cast<const double2 *>(gp),
+                *n2 = reinterpret_cast<const double2 *>(gn);
+  double l0 = 0.0, l1 = 0.0, p0 = 0.0, p1 = 0.0, n0 = 0.0, n1 = 0.0;
 #pragma unroll
   for (int c2 = 0; c2 < (D + 1) / 2; c2++) {
-    const double2 v = g2[c2];
-    s0 = fma(y[2 * c2], v.x, s0);
-    if (2 * c2 + 1 < D) s1 = fma(y[2 * c2 + 1], v.y, s1);
+    const double2 vp = p2[c2], vn = n2[c2];
+    p0 = fma(y[2 * c2], vp.x, p0);
+    n0 = fma(y[2 * c2], vn.x, n0);
+    if (WITH_L) {
+      const double2 vl = l2[c2];
+      l0 = fma(y[2 * c2], vl.x, l0);
+      if (2 * c2 + 1 < D) l1 = fma(y[2 * c2 + 1], vl.y, l1);
+    }
+    if (2 * c2 + 1 < D) {
+      p1 = fma(y[2 * c2 + 1], vp.y, p1);
+      n1 = fma(y[2 * c2 + 1], vn.y, n1);
+    }
   }
-  return s0 + s1;
+  dl = l0 + l1; dp = p0 + p1; dn = n0 + n1;
 }
 
 constexpr int kNbInline = 6;   // neighbour slots handled in the straight-line part (hex lattice degree); the rest in a loop
@@ -143,6 +163,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   int32_t *well = reinterpret_cast<int32_t *>(wbase + L.ell), *worig = reinterpret_cast<int32_t *>(wbase + L.orig);
   double *wst = reinterpret_cast<double *>(wbase + L.wst);
   uint8_t *zst = wbase + L.zst;
+  double *skacc = reinterpret_cast<double *>(wbase + L.skacc);
   double *cfold = reinterpret_cast<double *>(smraw + L.shared_bytes);   // + warp * warp_stride / 8
   const int fold_stride = L.warp_stride / 8;
 
@@ -159,8 +180,14 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       s_c[e] = Pm[a.PL.c + e];
       if (TDIST) s_cL[e] = Pm[a.PL.cL + e];
     }
-    if (TDIST)
-      for (int e = tid; e < NP + (NP & 1); e += kBlock) s_PL[e] = e < NP ? Pm[a.PL.PL + e] : 0.0;
+    if (TDIST) {   // packed Lambda, permuted from k_param's row-major order to column-major (quadform_cols)
+      for (int e = tid; e < NP; e += kBlock) {
+        int pa, pb;
+        pair_from_index(e, D, pa, pb);
+        s_PL[colpacked_index(pa, pb)] = Pm[a.PL.PL + e];
+      }
+      if (tid == 0 && (NP & 1)) s_PL[NP] = 0.0;
+    }
     for (int e = tid; e <= kMaxDeg; e += kBlock) s_pot[e] = e ? a.gamma / e * 2 : 0.0;   // (gamma / |N_j|) * 2 as at :289
     if (TDIST)
       for (int e = tid; e < 128; e += kBlock) log_table_entry(e, s_logtab[e]);
@@ -198,6 +225,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     const int nsub = (count + 31) >> 5;
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    for (int e = lane; e < q * DP; e += 32) skacc[e] = 0.0;
     double hp_acc = 0.0, nacc = 0.0, lw_m = 1.0;
     int lw_e = 0;
     double C[NTILES][2], CH[NT][NH][2];
@@ -262,15 +290,15 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
           for (int c = 0; c < D; c++)
             y[c] = *reinterpret_cast<const double *>(yb + c * kRowB + (my_chunk ^ ((c & 7) << 4)));
         }
-        double scale = 0.0;
+        double scale = 0.0, bL, dp, dn;
+        dot3<D, TDIST>(y, s_gL + zk * RS, s_g + zk * RS, s_g + zn * RS, bL, dp, dn);
         if (TDIST) {
           // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518)
-          const double aL = quadform2<D>(y, s_PL);
-          const double bL = dot2<D>(y, s_gL + zk * RS);
+          const double aL = quadform_cols<D>(y, s_PL);
           scale = 2.0 / ((aL - 2.0 * bL + s_cL[zk]) + 4.0);
         }
-        const double lin_p = s_c[zk] - 2.0 * dot2<D>(y, s_g + zk * RS);
-        const double lin_n = s_c[zn] - 2.0 * dot2<D>(y, s_g + zn * RS);
+        const double lin_p = s_c[zk] - 2.0 * dp;
+        const double lin_n = s_c[zn] - 2.0 * dn;
         int deg = 0, cp = 0, cn = 0;
 #pragma unroll
         for (int e = 0; e < kNbInline; e++) {
@@ -334,33 +362,59 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       }
       if (!dry) {
         // ---- fold this warp's 32 spots into its output tiles (FP64 tensor pipe) ---------------------
+        // DMMA runs on the same pipe as DFMA at the same FMA rate (measured), so every DMMA saved is time saved.
+        // The label tiles spend 8x the useful work (one label per spot, eight columns per tile); when all spots of
+        // the sub-tile carry ONE label k -- the common case on spatially coherent data -- their result is already in
+        // the second moments: column d of U (w U)^T (the constant-1 row) is sum_j w_j y_j and sum_j w_j of the
+        // sub-tile.  Its increment over this sub-tile is added to cluster k's sums; mixed sub-tiles use the label tiles.
         wst[lane] = wj;
         zst[lane] = (uint8_t) zfinal;
+        const int zf0 = __shfl_sync(0xffffffffu, zfinal, 0);
+        const bool uniform = do_pairs && __all_sync(0xffffffffu, !active || zfinal == zf0);
         __syncwarp();
+        // tile (i, NT-1) has index i*NT - i(i-1)/2 + NT-1-i in the upper-triangular enumeration
+        double snap[NT];
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-          // spot 4 g + lq: half g >> 2, column 4 (g & 3) + lq, i.e. chunk 2 (g & 3) + (lq >> 1)
-          const unsigned char *fb = ycur + (g >> 2) * YBOX + frag_row + (frag_sw ^ ((g & 3) << 5)) + frag_lo;
-          double f[NT];
+        for (int i = 0; i < NT; i++) snap[i] = C[i * NT - i * (i - 1) / 2 + (NT - 1 - i)][D & 1];
+        if (do_pairs) {
 #pragma unroll
-          for (int i = 0; i < NT; i++) f[i] = *reinterpret_cast<const double *>(fb + i * 8 * kRowB);
-          const double wt = wst[4 * g + lq];
-          const int zt = zst[4 * g + lq];
-          if (do_pairs) {
-            double b[NT];
+          for (int g = 0; g < 8; g++) {
+            // spot 4 g + lq: half g >> 2, column 4 (g & 3) + lq, i.e. chunk 2 (g & 3) + (lq >> 1)
+            const unsigned char *fb = ycur + (g >> 2) * YBOX + frag_row + (frag_sw ^ ((g & 3) << 5)) + frag_lo;
+            const double wt = wst[4 * g + lq];
+            double f[NT], b[NT];
 #pragma unroll
-            for (int i = 0; i < NT; i++) b[i] = f[i] * wt;
+            for (int i = 0; i < NT; i++) {
+              f[i] = *reinterpret_cast<const double *>(fb + i * 8 * kRowB);
+              b[i] = f[i] * wt;
+            }
             int tix = 0;
 #pragma unroll
             for (int i = 0; i < NT; i++)
 #pragma unroll
               for (int jj = i; jj < NT; jj++) dmma_m8n8k4(C[tix++], f[i], b[jj]);
           }
+        }
+        if (uniform) {
+          if (lq == ((D & 7) >> 1)) {   // the lanes that hold column d of the tiles (i, NT-1)
 #pragma unroll
-          for (int h = 0; h < NH; h++) {
-            const double hv = zt == kc + 8 * h ? wt : 0.0;
+            for (int i = 0; i < NT; i++) {
+              const int row = 8 * i + kc;
+              if (row <= D) skacc[zf0 * DP + row] += C[i * NT - i * (i - 1) / 2 + (NT - 1 - i)][D & 1] - snap[i];
+            }
+          }
+        } else {
 #pragma unroll
-            for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][h], f[i], hv);
+          for (int g = 0; g < 8; g++) {
+            const unsigned char *fb = ycur + (g >> 2) * YBOX + frag_row + (frag_sw ^ ((g & 3) << 5)) + frag_lo;
+            const double wt = wst[4 * g + lq];
+            const int zt = zst[4 * g + lq];
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+              const double hv = zt == kc + 8 * h ? wt : 0.0;
+#pragma unroll
+              for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][h], *reinterpret_cast<const double *>(fb + i * 8 * kRowB), hv);
+            }
           }
         }
       }
@@ -400,7 +454,9 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       const int t = NTILES + (k >> 3) * NT + (r >> 3);
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < kWarps; w++) s += cfold[(size_t) w * fold_stride + t * 64 + (r & 7) * 8 + (k & 7)];
+      for (int w = 0; w < kWarps; w++)
+        s += cfold[(size_t) w * fold_stride + t * 64 + (r & 7) * 8 + (k & 7)] +
+             reinterpret_cast<const double *>(smraw + L.shared_bytes + (size_t) w * L.warp_stride + L.skacc)[k * DP + r];
       if (r < D) acc[a.SL.sk + k * D + r] = s;
       else acc[a.SL.nk + k] = s;
     }
