@@ -412,12 +412,20 @@ static const size_t kParamSmemMax = 220 * 1024;
 
 typedef void (*param_kernel_t)(ParamArgs, int, int);
 static param_kernel_t *param_kernel_table() {
+#ifdef BSB_PARAM_DEV   // development builds: only the dimensions of the benchmark configurations (compile time)
+  static param_kernel_t t[kMaxD + 1] = {k_param<0>};
+  for (int i = 1; i <= kMaxD; i++) t[i] = k_param<0>;
+  t[15] = k_param<15>;
+  t[20] = k_param<20>;
+  return t;
+#else
   static param_kernel_t t[kMaxD + 1] = {
       k_param<0>,  k_param<1>,  k_param<2>,  k_param<3>,  k_param<4>,  k_param<5>,  k_param<6>,  k_param<7>,  k_param<8>,
       k_param<9>,  k_param<10>, k_param<11>, k_param<12>, k_param<13>, k_param<14>, k_param<15>, k_param<16>, k_param<17>,
       k_param<18>, k_param<19>, k_param<20>, k_param<21>, k_param<22>, k_param<23>, k_param<24>, k_param<25>, k_param<26>,
       k_param<27>, k_param<28>, k_param<29>, k_param<30>, k_param<31>, k_param<32>};
   return t;
+#endif
 }
 
 void launch_param(const ParamArgs &a, cudaStream_t stream) {

@@ -74,11 +74,20 @@ __host__ __device__ inline FastSmem fast_smem_layout(int D, int q, int E, bool t
   return s;
 }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-               : "memory");
+// policy: L2 eviction hint.  Everything a sweep streams (PCs, neighbour ids, original ids) is read exactly once per
+// launch: evict-first keeps it from flushing what IS re-read -- the label field (neighbour gathers), the statistics
+// records and the code of k_param, which runs between two sweeps.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
 constexpr int fast_min_blocks(int D) { return D <= 16 ? 4 : (D <= 24 ? 3 : 2); }
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   const bool do_pairs = !(a.flags & SW_NO_PAIRS) && a.SL.nlT > 0;
   const int ell_rows = stats_only ? 0 : a.maxdeg;
   const uint32_t tx_bytes = (uint32_t) (2 * D * kRowB + (stats_only ? 0 : (ell_rows + 1) * kRowB));
+  const uint64_t stream_policy = l2_evict_first_policy();
   uint32_t ntile = 0;   // sub-tiles this warp has consumed: buffer = ntile & 1, barrier parity = (ntile >> 1) & 1
 
   // Swizzled addressing (SWIZZLE_128B: 16-byte chunk index XOR row mod 8).
@@ -240,11 +250,11 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       if (lane == 0) {
         const int gi = begin + 32 * sub;
         mbar_arrive_expect_tx(mbar + buf, tx_bytes);
-        tma_load_2d(ybuf + (2 * buf) * YBOX, &maps.y, gi, 0, mbar + buf);
-        tma_load_2d(ybuf + (2 * buf + 1) * YBOX, &maps.y, gi + 16, 0, mbar + buf);
+        tma_load_2d(ybuf + (2 * buf) * YBOX, &maps.y, gi, 0, mbar + buf, stream_policy);
+        tma_load_2d(ybuf + (2 * buf + 1) * YBOX, &maps.y, gi + 16, 0, mbar + buf, stream_policy);
         if (!stats_only) {
-          if (ell_rows) tma_load_2d(well + buf * ell_rows * 32, &maps.ell, gi, 0, mbar + buf);
-          tma_load_2d(worig + buf * 32, &maps.orig, gi, 0, mbar + buf);
+          if (ell_rows) tma_load_2d(well + buf * ell_rows * 32, &maps.ell, gi, 0, mbar + buf, stream_policy);
+          tma_load_2d(worig + buf * 32, &maps.orig, gi, 0, mbar + buf, stream_policy);
         }
       }
     };
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
             nacc += 1.0;
           }
           if (TDIST) {
-            a.w[j] = wj;
+            __stcs(a.w + j, wj);   // streaming store: written once per sweep, read only by snapshots
             // sum_j log w_j as a running product, renormalised only when it leaves [1e-150, 1e150]
             double m2 = lw_m * wj;
             if (!(m2 >= 1e-150 && m2 <= 1e150)) {
