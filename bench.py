@@ -30,6 +30,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+def load_synth():
+    """bayesspace_b200/synth.py (pure numpy) loaded by path: the reference arm must not import the product package,
+    which would map libbsb200.so into the process."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bsb200_synth", os.path.join(ROOT, "bayesspace_b200", "synth.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 ALGO_NOTE = "8d + 4 (z read) + 4 (z write) + 4*deg (neighbour z) + 8 (w write, t model) bytes per spot-update"
 
 
@@ -153,11 +163,13 @@ class ClockSampler:
 
 def ncu_traffic(name):
     """dram__bytes_read.sum + dram__bytes_write.sum per sweep launch from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r1_sweep_%s_ncu.json" % name)
-    try:
-        return float(json.load(open(p))["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    for rnd in ("r2", "r1"):
+        p = os.path.join(ROOT, "profiles", "%s_sweep_%s_ncu.json" % (rnd, name))
+        try:
+            return float(json.load(open(p))["traffic_bytes_per_launch"]), "profiles/%s_sweep_%s_ncu.json" % (rnd, name)
+        except Exception:
+            pass
+    return None, None
 
 
 def build_workload(name):
@@ -210,13 +222,20 @@ def cpu_baseline(w, csr, budget_s=15.0, sweeps=2):
                       (sweeps, n_s, n_s // w.cols, t)}, n_s
 
 
+def reference_workload(name):
+    """The same synthetic workload built WITHOUT the product: lattice from the oracle's .find_neighbors restatement."""
+    from oracle import oracle as O
+    synth = load_synth()
+    w = synth.make_workload(name)
+    csr = O.lattice_neighbors(w.array_row, w.array_col, w.platform)
+    return w, csr
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from bayesspace_b200 import synth
-    import bayesspace_b200 as B
-    w, csr, _ = build_workload(args.workload)
+    w, csr = reference_workload(args.workload)
     K, W = max(1, args.steps), max(0, args.warmup)
     # bounded sample sized so that K + W sweeps take about a minute on one host core
     base, n_cal = cpu_baseline(w, csr, budget_s=3.0, sweeps=1)
@@ -236,6 +255,7 @@ def run_reference(args):
     t = time.perf_counter() - t0
     val = n_s * K / t
     sample = "%d sweeps over the first %d spots (%d lattice rows) of %s" % (K, n_s, n_s // w.cols, args.workload)
+    assert "bayesspace_b200" not in sys.modules, "the reference arm must not load the product"
     line = {"impl": "reference", "metric": "spot-updates/s", "value": val, "unit": "spot-updates/s",
             "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -307,13 +327,124 @@ def deconv_workload(B, device, peak, with_cpu):
     return res
 
 
+def bitexact_check(B, dist, rank, world, local):
+    """Short sharded-vs-alone comparison on every rank before the timed runs: the spot-sharded chain must reproduce
+    the 1-GPU chain bit for bit (labels, weights, mu, lambda, plogLik) -- the north_star's level-1 claim."""
+    from bayesspace_b200 import samplers, synth
+    ok = True
+    for name, shape, fname in (("small_sq", (96, 64), "iterate_t"), ("small_hex", (64, 48), "iterate")):
+        w = synth.make_workload(name, n_override=shape)
+        _, csr = B.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
+        colour = B.colour_lattice(w.array_row, w.array_col, w.platform)
+        a = (w.Y, csr, 16, 4, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0, w.alpha, w.beta)
+        ids = [samplers.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        f = getattr(B, fname)
+        alone = f(*a, seed=99, colour=colour, groups=64, device=local)
+        shard = f(*a, seed=99, colour=colour, groups=64, device=local, world=world, rank=rank, comm_id=ids[0])
+        lo, hi = shard["_info"]["own"]
+        ok = ok and np.array_equal(shard["z"][:, lo:hi], alone["z"][:, lo:hi])
+        if "weights" in alone:
+            ok = ok and np.array_equal(shard["weights"][1:, lo:hi], alone["weights"][1:, lo:hi])
+        for key in ("mu", "lambda"):
+            ok = ok and np.array_equal(shard[key], alone[key])
+        ok = ok and np.array_equal(shard["plogLik"][1:], alone["plogLik"][1:])
+    import torch
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def qtune_sweep(B, dist, rank, world, local, with_oracle):
+    """BASELINE configs[4], second half: qTune's q sweep (R/qTune.R:102-119) -- cluster() for q = 2..15, normal model,
+    equal precision, nrep = 1000, burn.in = 100 on the C2 lattice, ONE CHAIN PER GPU with no communication (the
+    reference fans the q values out over BiocParallel workers).  Returns wall time, mean plogLik per q, and for one q
+    a comparison with the CPU oracle run in the same visiting order."""
+    from bayesspace_b200 import synth
+    w = synth.make_workload("c2")
+    _, csr = B.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
+    colour = B.colour_lattice(w.array_row, w.array_col, w.platform)
+    qs, nrep, burn = list(range(2, 16)), 1000, 100
+    mine = [q for i, q in enumerate(qs) if i % world == rank]
+    res = {}
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for q in mine:
+        init = ((w.truth - 1) % q + 1).astype(np.int32)      # every label present; cluster() is given an init as in qTune
+        out = B.cluster(w.Y, q, csr, init=init, model="normal", precision="equal", mu0=w.mu0, lambda0=w.lambda0,
+                        gamma=w.gamma, alpha=w.alpha, beta=w.beta, nrep=nrep, thin=100, seed=1000 + q, device=local,
+                        colour=colour)
+        res[q] = float(np.mean(out["plogLik"][burn:nrep]))   # mean(plogLik[(burn.in+1):nrep]), R/qTune.R:113
+    wall = time.perf_counter() - t0
+    if dist:
+        import torch
+        t = torch.tensor([wall], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        allres = [None] * world
+        dist.all_gather_object(allres, res)
+        res = {k: v for r in allres for k, v in r.items()}
+    out = {"config": "qTune q sweep: q = 2..15, normal model, equal precision, nrep = 1000, burn.in = 100, C2 lattice "
+                     "(4,992 spots, d = 15), one chain per GPU, no communication",
+           "n_gpus": world, "wall_s": wall, "chains": len(qs), "sweeps_per_s_all_chains": len(qs) * (nrep - 1) / wall,
+           "mean_plogLik": {str(q): res[q] for q in sorted(res)}}
+    if with_oracle and rank == 0:
+        from oracle import oracle as O
+        q, n2 = 4, 60
+        init = ((w.truth - 1) % q + 1).astype(np.int32)
+        order = np.lexsort((np.arange(w.n), colour[0])).astype(np.int32)
+        a = (w.Y, csr, n2, 10, w.n, w.d, w.gamma, q, init, w.mu0, w.lambda0, w.alpha, w.beta)
+        got = B.iterate(*a, seed=1004, device=local, colour=colour)
+        ref = O.iterate(*a, seed=1004, order=order)
+        out["oracle_check"] = {"q": q, "nrep": n2, "labels_identical": bool(np.array_equal(got["z"], ref["z"])),
+                               "plogLik_max_rel_err": float(np.max(np.abs(got["plogLik"][1:] - ref["plogLik"][1:]) /
+                                                                   np.abs(ref["plogLik"][1:])))}
+    return out
+
+
+def sharded_extra(B, dist, rank, world, local, name, K, W):
+    """One more configuration spot-sharded over the job's GPUs (C4 beside the default C5): ms per sweep, max over ranks."""
+    from bayesspace_b200 import samplers
+    w, csr, colour = build_workload(name)
+    ids = [samplers.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ch = B.Chain(*chain_args(w, csr, W + 2 * K + 64, 100), model=w.model, precision=w.precision, seed=149, device=local,
+                 colour=colour, world=world, rank=rank, comm_id=ids[0])
+    ch.run(W)
+    import torch
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = ch.run(K)
+    t = torch.tensor([ms], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    prof = ch.profile(min(K, 50))
+    ch.close()
+    mean_deg = len(csr[1]) / w.n
+    per_launch = prof["sweep_ms"] / max(1, prof["sweep_launches"])
+    peak, _ = measured_peak()
+    return {"config": workload_config(w, name), "n_gpus": world, "ms_per_step": ms / K,
+            "spot_updates_per_s": w.n * K / (ms * 1e-3), "sweep_launch_ms": per_launch,
+            "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50)),
+            "halo_exchange_ms_per_iter": prof["halo_ms"] / max(1, min(K, 50)),
+            "hbm_frac_sweep_kernel": (algorithmic_bytes(w.d, mean_deg, w.model == "t") * (w.n / world) / colour[1]) /
+                                     (per_launch * 1e-3) / 1e9 / peak}
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout and would precede the JSON line
+        if os.environ.get("BSB200_COMM") == "nccl":
+            # the communicator lines stay checkable, but in a file: NCCL's banner on stdout would precede the JSON line
+            os.environ.setdefault("NCCL_DEBUG", "INFO")
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl_%h_%p.log"))
+        else:
+            os.environ["NCCL_DEBUG"] = "WARN"   # torch's own NCCL must not print a banner before the JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -339,6 +470,7 @@ def run_gpu(args):
         dist.broadcast_object_list(ids, src=0)
         return ids[0]
 
+    bitexact = bitexact_check(B, dist, rank, world, local) if sharded else None
     shard_kw = dict(world=world, rank=rank, comm_id=comm_id()) if sharded else {}
     ch = B.Chain(*chain_args(w, csr, nrep, thin), model=w.model, precision=w.precision,
                  seed=149 + (0 if sharded else rank), device=local, colour=colour, **shard_kw)
@@ -379,6 +511,11 @@ def run_gpu(args):
         t = torch.tensor([e2e_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    extra = {}
+    if sharded and args.others:
+        extra["c4"] = sharded_extra(B, dist, rank, world, local, "c4", 300, 10)
+    if args.others:
+        extra["qtune"] = qtune_sweep(B, dist if world > 1 else None, rank, world, local, not args.no_cpu)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -399,14 +536,16 @@ def run_gpu(args):
                    "stores into peer GPU memory from the library's own kernels (CUDA IPC over NVLink, epoch flags)")
                 if sharded else ("1 chain per GPU (replicas, no collective)" if world > 1 else "single chain, 1 GPU")),
                 sweeps_per_s=(1 if sharded or world == 1 else world) * K / (ms * 1e-3), colours=colour[1]),
-            "roofline": {"bound": "hbm", "kernel": "k_sweep<%d,t,shared>" % w.d, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(args.workload),
-                         "traffic_source": "profiles/r1_sweep_%s_ncu.json (ncu --set full, bytes per launch)" % args.workload,
+            "roofline": {"bound": "hbm", "kernel": "k_sweep_fast<%d, t, NH=%d>" % (w.d, (w.q + 7) // 8), "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(args.workload)[0],
+                         "traffic_source": "%s (ncu --set full, bytes per launch)" % ncu_traffic(args.workload)[1],
                          "algorithmic_bytes_per_spot_update": Bspot, "bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": sweep_ms_per_launch, "formula": ALGO_NOTE,
                          "param_kernel_ms_per_iter": prof["param_ms"] / max(1, min(K, 50)),
                          "halo_exchange_ms_per_iter": prof["halo_ms"] / max(1, min(K, 50))},
             "gpu_launches": int(launches), "clocks": ck}
+    if bitexact is not None:
+        line["bitexact"] = bitexact   # sharded chain == 1-GPU chain, bit for bit, checked on every rank before timing
     nsnap = (e2e_iters + 1) // 100
     h2d = w.n * w.d * 8 + w.n * 4 + len(csr[1]) * 4 + (w.n + 1) * 8
     d2h = nsnap * w.n * (4 + (8 if w.model == "t" else 0)) + (e2e_iters + 1) * 8
@@ -435,7 +574,10 @@ def run_gpu(args):
             if not args.no_cpu:
                 others[name]["cpu_baseline"], _ = cpu_baseline(w2, csr2, budget_s=8.0)
         others["c3"] = deconv_workload(B, local, peak, not args.no_cpu)
+        others.update(extra)
         line["other_workloads"] = others
+    elif extra:
+        line["other_workloads"] = extra
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

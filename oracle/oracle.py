@@ -206,6 +206,33 @@ _ERR = {1: "Invalid arguments!", 2: "Error in finding neighbors of subspots!", 3
         6: "NA in probability vector", 7: "adaptive Cholesky failed", 8: "degree > 4"}
 
 
+def scan_fixed(variant, Y, df_j, gamma, q, init, mu, lam, niter, seed=0, order=None, compat=COMPAT_REFERENCE):
+    """niter z (and w) scans of a cluster sampler with FIXED mu (q x d) and lambda (d x d, or q x d x d for the VVV
+    samplers): the label-update Markov kernel alone.  Returns (histogram over the q^n label configurations, coded
+    sum_j (z_j - 1) q^j; mean of the weights)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    n, d = Y.shape
+    v = VARIANTS[variant] if isinstance(variant, str) else variant
+    ptr, idx = df_j if isinstance(df_j, tuple) else csr_from_lists(df_j)
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    lam = np.asarray(lam, dtype=np.float64)
+    lam3 = lam if lam.ndim == 3 else lam[None]
+    lb = np.concatenate([_colmajor(m) for m in lam3])
+    sb = np.concatenate([_colmajor(np.linalg.inv(m)) for m in lam3])
+    yb, mub, zb = _colmajor(Y), _f64(mu).ravel(), np.ascontiguousarray(init, dtype=np.int32)
+    ob = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    hist = np.zeros(q ** n, dtype=np.int64)
+    wm = np.zeros(n)
+    rc = lib().orc_scan_fixed(v, C.c_uint32(compat), _p(yb, C.c_double), C.c_int64(n), d, q, _p(ptr, C.c_int64),
+                              _p(idx, C.c_int32), C.c_double(gamma), _p(zb, C.c_int32), _p(mub, C.c_double),
+                              _p(lb, C.c_double), _p(sb, C.c_double), C.c_uint64(seed), _p(ob, C.c_int32), int(niter),
+                              _p(hist, C.c_int64), _p(wm, C.c_double))
+    if rc:
+        raise RuntimeError("oracle error %d" % rc)
+    return hist, wm
+
+
 def _run_cluster(variant, Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta,
                  seed=0, order=None, compat=COMPAT_REFERENCE):
     Y = np.asarray(Y, dtype=np.float64)

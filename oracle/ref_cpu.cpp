@@ -411,6 +411,70 @@ struct ClusterIO {
 
 inline double yat(const double *Y, int64_t n, int64_t j, int c) { return Y[(size_t) c * n + j]; }
 
+// One z (and w) scan of the cluster samplers (:272-306, :392-429, :507-552, :646-694) with the parameters of
+// iteration i: the body of the reference's `for (j = 0; j < n; j++)` loop, over io.order when given.
+// Shared by run_cluster() and by the fixed-parameter scan used to pin the target distribution (orc_scan_fixed).
+int scan_zw(const ClusterIO &io, int i, const Rng &rng, std::vector<int32_t> &z, vecd &w, const vecd &mu,
+            const vecd &mu_long, const std::vector<vecd> &lambda, const std::vector<vecd> &sigma, vecd &plogLikj) {
+  const bool vvv = io.variant == 1 || io.variant == 3, tdist = io.variant >= 2;
+  const int64_t n = io.n;
+  const int d = io.d, q = io.q;
+  const size_t dd = (size_t) d * d;
+  const bool q1 = io.compat & COMPAT_Q1, q3 = (io.compat & COMPAT_Q3) && io.variant == 1;
+  vecd sigw(dd);
+  const double w_alpha = (double) ((d + 4) / 2);   // Q2: integer division
+  for (int64_t t = 0; t < n; t++) {
+    const int64_t j = io.order ? io.order[t] : t;
+    const int z_prev = z[j];
+    vecd yj(d);
+    for (int c = 0; c < d; c++) yj[c] = yat(io.Y, n, j, c);
+    if (tdist) {
+      const vecd &lam = lambda[vvv ? z_prev - 1 : 0];
+      double quad = 0.0;
+      for (int a = 0; a < d; a++) {
+        double s = 0.0;
+        for (int b = 0; b < d; b++) s += at(lam, d, a, b) * (yj[b] - mu_long[(size_t) j * d + b]);
+        quad += (yj[a] - mu_long[(size_t) j * d + a]) * s;
+      }
+      const double w_beta = 2.0 / (quad + 4.0);
+      w[j] = gamma_spot(rng, (uint32_t) j, (uint32_t) i, w_alpha, w_beta, spot_draw(rng, (uint32_t) j, (uint32_t) i).u_first);
+    }
+    const SpotDraw dr = spot_draw(rng, (uint32_t) j, (uint32_t) i);
+    const double u_acc = dr.u_acc;
+    const int z_new = propose_label_bits(z_prev, q, dr.prop_bits);
+    const int dg = io.g.deg(j);
+    const int32_t *nb = io.g.nb(j);
+    double h_prev = 0.0, h_new = 0.0;
+    if (dg != 0) {
+      int c_prev = 0, c_new = 0;
+      for (int e = 0; e < dg; e++) {
+        if (q3) c_prev += (nb[e] == z_prev);   // Q3 (:404): neighbour INDEX compared to label
+        else c_prev += (z[nb[e]] == z_prev);
+        c_new += (z[nb[e]] == z_new);
+      }
+      h_prev = io.gamma / dg * 2 * c_prev;
+      h_new = io.gamma / dg * 2 * c_new;
+    }
+    const vecd *sp = &sigma[vvv ? z_prev - 1 : 0], *sn = &sigma[vvv ? z_new - 1 : 0];
+    if (tdist) {
+      for (size_t e = 0; e < dd; e++) sigw[e] = (*sp)[e] / w[j];
+      h_prev += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_prev - 1) * d], sigw, d, q1);
+      if (vvv)
+        for (size_t e = 0; e < dd; e++) sigw[e] = (*sn)[e] / w[j];
+      h_new += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_new - 1) * d], sigw, d, q1);
+    } else {
+      h_prev += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_prev - 1) * d], *sp, d, q1);
+      h_new += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_new - 1) * d], *sn, d, q1);
+    }
+    double prob = std::exp(h_new - h_prev);
+    if (prob > 1) prob = 1;
+    if (std::isnan(prob)) return 6;   // Rcpp sample() errors on NA probabilities
+    if (sample_two(prob, u_acc)) z[j] = z_new;
+    plogLikj[j] = h_prev;
+  }
+  return 0;
+}
+
 // The four cluster samplers share one body; `vvv` and `tdist` select the reference function.
 int run_cluster(const ClusterIO &io) {
   const bool vvv = io.variant == 1 || io.variant == 3, tdist = io.variant >= 2;
@@ -419,7 +483,6 @@ int run_cluster(const ClusterIO &io) {
   const int nsnap = nrep / thin + 1, nl = vvv ? q : 1;
   const size_t dd = (size_t) d * d;
   const Rng rng(io.seed);
-  const bool q1 = io.compat & COMPAT_Q1, q3 = (io.compat & COMPAT_Q3) && io.variant == 1;
   const double nan = std::numeric_limits<double>::quiet_NaN();
 
   vecd lambda0(io.lambda0, io.lambda0 + dd), sigma0;
@@ -439,7 +502,7 @@ int run_cluster(const ClusterIO &io) {
 
   vecd lm0(d);
   matvec(lambda0, io.mu0, d, lm0.data());
-  vecd P(dd), var, rhs(d), mean(d), ysum(d), S(dd), Sc, VS(dd), sigw(dd);
+  vecd P(dd), var, rhs(d), mean(d), ysum(d), S(dd), Sc, VS(dd);
 
   for (int i = 1; i < nrep; i++) {
     // ---- update mu (:246-258, :359-372, :478-493, :609-625)
@@ -485,55 +548,9 @@ int run_cluster(const ClusterIO &io) {
       if (!inv_general(lambda[kk], d, sigma[kk])) return 5;
     }
     // ---- update z (and w) (:272-306, :392-429, :507-552, :646-694)
-    const double w_alpha = (double) ((d + 4) / 2);   // Q2: integer division
-    for (int64_t t = 0; t < n; t++) {
-      const int64_t j = io.order ? io.order[t] : t;
-      const int z_prev = z[j];
-      vecd yj(d);
-      for (int c = 0; c < d; c++) yj[c] = yat(io.Y, n, j, c);
-      if (tdist) {
-        const vecd &lam = lambda[vvv ? z_prev - 1 : 0];
-        double quad = 0.0;
-        for (int a = 0; a < d; a++) {
-          double s = 0.0;
-          for (int b = 0; b < d; b++) s += at(lam, d, a, b) * (yj[b] - mu_long[(size_t) j * d + b]);
-          quad += (yj[a] - mu_long[(size_t) j * d + a]) * s;
-        }
-        const double w_beta = 2.0 / (quad + 4.0);
-        w[j] = gamma_spot(rng, (uint32_t) j, (uint32_t) i, w_alpha, w_beta, spot_draw(rng, (uint32_t) j, (uint32_t) i).u_first);
-      }
-      const SpotDraw dr = spot_draw(rng, (uint32_t) j, (uint32_t) i);
-      const double u_acc = dr.u_acc;
-      const int z_new = propose_label_bits(z_prev, q, dr.prop_bits);
-      const int dg = io.g.deg(j);
-      const int32_t *nb = io.g.nb(j);
-      double h_prev = 0.0, h_new = 0.0;
-      if (dg != 0) {
-        int c_prev = 0, c_new = 0;
-        for (int e = 0; e < dg; e++) {
-          if (q3) c_prev += (nb[e] == z_prev);   // Q3 (:404): neighbour INDEX compared to label
-          else c_prev += (z[nb[e]] == z_prev);
-          c_new += (z[nb[e]] == z_new);
-        }
-        h_prev = io.gamma / dg * 2 * c_prev;
-        h_new = io.gamma / dg * 2 * c_new;
-      }
-      const vecd *sp = &sigma[vvv ? z_prev - 1 : 0], *sn = &sigma[vvv ? z_new - 1 : 0];
-      if (tdist) {
-        for (size_t e = 0; e < dd; e++) sigw[e] = (*sp)[e] / w[j];
-        h_prev += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_prev - 1) * d], sigw, d, q1);
-        if (vvv)
-          for (size_t e = 0; e < dd; e++) sigw[e] = (*sn)[e] / w[j];
-        h_new += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_new - 1) * d], sigw, d, q1);
-      } else {
-        h_prev += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_prev - 1) * d], *sp, d, q1);
-        h_new += dmvnrm_arma_fast(yj.data(), &mu[(size_t) (z_new - 1) * d], *sn, d, q1);
-      }
-      double prob = std::exp(h_new - h_prev);
-      if (prob > 1) prob = 1;
-      if (std::isnan(prob)) return 6;   // Rcpp sample() errors on NA probabilities
-      if (sample_two(prob, u_acc)) z[j] = z_new;
-      plogLikj[j] = h_prev;
+    {
+      const int rc = scan_zw(io, i, rng, z, w, mu, mu_long, lambda, sigma, plogLikj);
+      if (rc) return rc;
     }
     double pl = 0.0;
     for (int64_t j = 0; j < n; j++) pl += plogLikj[j];
@@ -995,6 +1012,43 @@ int orc_h_values(int variant, uint32_t compat, const double *Y, int64_t n, int d
     hn += dmvnrm_arma_fast(yj.data(), mu + (size_t) (zn - 1) * d, sg, d, q1);
     h_prev[j] = hp;
     h_new[j] = hn;
+  }
+  return 0;
+}
+
+// niter z (and w) scans with FIXED mu / lambda (sigma = inverse given by the caller): the Markov kernel of the label
+// update alone.  hist[c] counts how often configuration c = sum_j (z_j - 1) q^j was seen after a scan (n small).
+int orc_scan_fixed(int variant, uint32_t compat, const double *Y, int64_t n, int d, int q, const int64_t *nbr_ptr,
+                   const int32_t *nbr_idx, double gamma, const int32_t *init, const double *mu_in,
+                   const double *lambda_in, const double *sigma_in, uint64_t seed, const int32_t *order, int niter,
+                   int64_t *hist, double *w_mean) {
+  const bool vvv = variant == 1 || variant == 3;
+  const int nl = vvv ? q : 1;
+  const size_t dd = (size_t) d * d;
+  ClusterIO io{variant, Y, n, d, q, Csr{nbr_ptr, nbr_idx}, niter + 1, 1, gamma, init, nullptr, nullptr, 0.0, 0.0, seed, order,
+               compat, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<int32_t> z(init, init + n);
+  vecd w((size_t) n, 1.0), mu(mu_in, mu_in + (size_t) q * d), mu_long((size_t) n * d), plogLikj((size_t) n);
+  std::vector<vecd> lambda(nl), sigma(nl);
+  for (int k = 0; k < nl; k++) {
+    lambda[k].assign(lambda_in + k * dd, lambda_in + (k + 1) * dd);
+    sigma[k].assign(sigma_in + k * dd, sigma_in + (k + 1) * dd);
+  }
+  const Rng rng(seed);
+  try {
+    for (int i = 1; i <= niter; i++) {
+      for (int64_t j = 0; j < n; j++)
+        for (int c = 0; c < d; c++) mu_long[(size_t) j * d + c] = mu[(size_t) (z[j] - 1) * d + c];
+      const int rc = scan_zw(io, i, rng, z, w, mu, mu_long, lambda, sigma, plogLikj);
+      if (rc) return rc;
+      int64_t code = 0, mult = 1;
+      for (int64_t j = 0; j < n; j++) { code += (z[j] - 1) * mult; mult *= q; }
+      hist[code]++;
+      if (w_mean)
+        for (int64_t j = 0; j < n; j++) w_mean[j] += w[j] / niter;
+    }
+  } catch (...) {
+    return 99;
   }
   return 0;
 }

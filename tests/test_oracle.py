@@ -335,3 +335,73 @@ def test_chromatic_visiting_order_in_both_restatements(oracle):
                                  np.asarray(w.mu0), np.asarray(w.lambda0), w.alpha, w.beta, 9, order=order)
     assert np.array_equal(gotd["z"], refd["z"]) and np.array_equal(gotd["Ychange"][1:], refd["Ychange"][1:])
     assert np.allclose(gotd["plogLik"][1:], refd["plogLik"][1:], rtol=1e-11)
+
+
+# ---- the label kernel against an enumerated posterior ----------------------------------------------------------
+def _cycle(n):
+    return [np.array(sorted({(j - 1) % n, (j + 1) % n}), dtype=np.int32) for j in range(n)]
+
+
+def _enumerate_posterior(logf, n, q, gamma, nbrs):
+    """pi(z) ~ exp(sum_j log f_{z_j}(y_j) + gamma * #{edges with equal labels}) over all q^n configurations, coded
+    sum_j (z_j - 1) q^j.  On a graph whose degrees are all 2 the conditional the sampler uses,
+    (gamma / |N_j|) * 2 * #{u in N_j: z_u = k} (src/cluster.cpp:289), is the conditional of exactly this joint."""
+    edges = {(min(j, int(u)), max(j, int(u))) for j in range(n) for u in nbrs[j]}
+    logp = np.zeros(q ** n)
+    for code in range(q ** n):
+        z = [(code // q ** j) % q for j in range(n)]
+        logp[code] = sum(logf[j, z[j]] for j in range(n)) + gamma * sum(z[a] == z[b] for a, b in edges)
+    p = np.exp(logp - logp.max())
+    return p / p.sum()
+
+
+@pytest.mark.parametrize("n,q,chromatic", [(6, 2, False), (6, 2, True), (5, 3, False), (5, 3, True)])
+def test_label_kernel_targets_the_enumerated_posterior_normal(oracle, n, q, chromatic):
+    """Pins WHAT the restated z scan samples, independently of how src/cluster.cpp:272-306 was read: with mu and
+    lambda held fixed, the long-run frequencies of all q^n label configurations must match the exact Potts x Gaussian
+    posterior (density in the reference's form, quirk Q1 included), for the reference's sequential scan and for
+    the colour-class order the CUDA path uses."""
+    rng = np.random.default_rng(10 * n + q)
+    d, gamma = 2, 1.1
+    mu = rng.normal(size=(q, d)) * 0.9
+    A = rng.normal(size=(d, d))
+    Sig = A @ A.T / d + 0.6 * np.eye(d)
+    Y = mu[rng.integers(0, q, size=n)] + rng.normal(size=(n, d))
+    nbrs = _cycle(n)
+    R = np.linalg.cholesky(Sig).T                   # Q1: quadratic form with (R R^T)^-1, R = chol_upper(Sigma)
+    M = np.linalg.inv(R @ R.T)
+    logf = np.array([[-np.log(np.diag(R)).sum() - d / 2 * np.log(2 * np.pi) - 0.5 * (y - m) @ M @ (y - m) for m in mu]
+                     for y in Y])
+    exact = _enumerate_posterior(logf, n, q, gamma, nbrs)
+    order = None
+    if chromatic:   # a proper colouring of the cycle, classes visited in sequence
+        col = np.array([j % 2 for j in range(n)]) if n % 2 == 0 else np.array([j % 2 for j in range(n - 1)] + [2])
+        order = np.lexsort((np.arange(n), col)).astype(np.int32)
+    niter = 120000
+    hist, _ = oracle.scan_fixed("iterate", Y, nbrs, gamma, q, rng.integers(1, q + 1, size=n), mu, np.linalg.inv(Sig),
+                                niter, seed=5, order=order)
+    freq = hist / niter
+    assert 0.5 * np.abs(freq - exact).sum() < 0.012          # total variation
+    top = np.argsort(exact)[-8:]
+    assert np.all(np.abs(freq[top] - exact[top]) < 6 * np.sqrt(exact[top] * (1 - exact[top]) * 4 / niter) + 1e-3)
+
+
+def test_label_and_weight_kernel_targets_the_student_t_posterior(oracle):
+    """t model with the quirks switched off (compat = 0; even d, so Q2's integer division is exact): alternating
+    w_j | z_j ~ Gamma((d+4)/2, scale 2 / (quad + 4)) (:513-518) with the label step on N(y; mu_k, Sigma / w_j) leaves the
+    label marginal Potts x multivariate-t_4 invariant; compared with its enumeration."""
+    rng = np.random.default_rng(77)
+    n, q, d, gamma = 6, 2, 2, 0.8
+    mu = rng.normal(size=(q, d))
+    A = rng.normal(size=(d, d))
+    Sig = A @ A.T / d + 0.5 * np.eye(d)
+    Y = mu[rng.integers(0, q, size=n)] + rng.standard_t(4, size=(n, d))
+    nbrs = _cycle(n)
+    logf = np.array([[stats.multivariate_t.logpdf(y, loc=m, shape=Sig, df=4) for m in mu] for y in Y])
+    exact = _enumerate_posterior(logf, n, q, gamma, nbrs)
+    niter = 150000
+    hist, wm = oracle.scan_fixed("iterate_t", Y, nbrs, gamma, q, np.ones(n, dtype=np.int32), mu, np.linalg.inv(Sig), niter,
+                                 seed=9, compat=0)
+    freq = hist / niter
+    assert 0.5 * np.abs(freq - exact).sum() < 0.015
+    assert np.all(wm > 0.2) and np.all(wm < 3.0)
