@@ -110,6 +110,13 @@ size_t sweep_smem_any(const KernelsForD &K, int tdist, int vvv, const SweepArgs 
   return use_fast(K, vvv, a) ? K.sweep_fast_smem(tdist, a) : K.sweep_smem(tdist, vvv, a);
 }
 
+size_t device_smem_limit() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+  return (size_t) v;
+}
+
 int select_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -619,6 +626,19 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     ch->have_maps = true;
   }
   mark("buffers");
+  // ---- the configuration must fit the shared memory of one CTA (sweep: per-cluster parameter blocks + tiles;
+  //      k_param: 3 q d + 4 d^2 doubles) -- say so instead of failing inside a launch
+  {
+    ch->SL = make_stat_layout(q, d, std::max(nlT, 1));
+    const size_t limit = device_smem_limit();
+    const size_t need_sweep = sweep_smem_any(K, ch->tdist, ch->vvv, ch->sweep_args(0, 0, 0));
+    const size_t need_param = param_smem_min(q, d);
+    if (limit && (need_sweep > limit || need_param > std::min<size_t>(limit, 220 * 1024)))
+      return fail(BSB200_ERR_UNSUPPORTED,
+                  "d = %d, q = %d, %s / %s precision needs %zu (sweep) / %zu (parameter update) bytes of shared memory per "
+                  "CTA, the device offers %zu: reduce q or d", d, q, ch->tdist ? "t" : "normal", ch->vvv ? "variable" : "equal",
+                  need_sweep, need_param, limit);
+  }
   // ---- statistics of the initial state -----------------------------------------------------------
   param_kernel_init();
   if (nlT == 0) {   // normal model, shared precision: sum_j y_j y_j^T never changes -> T_fixed
@@ -888,6 +908,12 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   if (out->weights && ch->tdist) {
     if (sharded) std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
     for (int64_t j = 0; j < n; j++) out->weights[j] = 1.0;
+  }
+  if (!sharded && args->thin == 1 && nsnap > 1) {
+    // iteration i is stored in row (i + 1) / thin: with thin = 1 the first iteration lands in row 2 and row 1 is never
+    // produced (it stays zero in the reference, src/cluster.cpp:310-313) -- do not leave the caller's bytes there
+    if (out->z) std::memset(out->z + n, 0, sizeof(int32_t) * n);
+    if (out->weights && ch->tdist) std::memset(out->weights + n, 0, sizeof(double) * n);
   }
   out->rows_done = 1;
   out->ncolours = ch->ord.ncol;

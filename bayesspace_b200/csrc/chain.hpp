@@ -55,5 +55,6 @@ constexpr int kOrderAlign = 32;   // alignment of the ranges in the cluster samp
 int choose_groups(int64_t n);
 int choose_segment(int64_t n, int ncol = 0, int d = 15);   // ncol = 0: the plain n-based rule (probes, deconvolution)
 void param_kernel_init();
+size_t param_smem_min(int q, int d);   // least dynamic shared memory k_param needs (one matrix per batch)
 
 }   // namespace bsb

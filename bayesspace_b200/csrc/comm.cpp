@@ -224,7 +224,10 @@ __device__ void wait_flag(const uint32_t *flag, uint32_t epoch, int *err, unsign
 // One CTA per neighbouring rank: store the boundary labels of the colour just swept into the neighbour's ghost
 // slots, release the neighbour's flag, then wait until the neighbour's own labels of this colour have landed here.
 // WAR safety: the slots written belong to the colour just swept, which the neighbour reads only in LATER phases,
-// and a rank can be at most one phase ahead of a neighbour because each phase ends with this wait.
+// and a rank can be at most one phase ahead of a neighbour because each phase ends with this wait.  The handshake
+// is SYMMETRIC: two ranks that exchange labels in ANY colour release and wait on each other in EVERY colour phase,
+// also when one direction (or both) carries no labels for that colour -- with one-sided legs (irregular graphs,
+// DSATUR colourings) the sender would otherwise run ahead and overwrite ghost labels its neighbour still reads.
 __global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const uint8_t *z, const int32_t *send_pos,
                                                    const int32_t *send_dst, uint32_t *counters, int world, int *err,
                                                    unsigned long long timeout_ns) {
@@ -233,16 +236,10 @@ __global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const ui
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (L.s1 > L.s0) {
-      const uint32_t e = counters[L.peer] + 1u;
-      counters[L.peer] = e;
-      st_release_sys(L.peer_flag, e);
-    }
-    if (L.nrecv > 0) {
-      const uint32_t e = counters[world + L.peer] + 1u;
-      counters[world + L.peer] = e;
-      wait_flag(L.my_flag, e, err, timeout_ns);
-    }
+    const uint32_t e = counters[L.peer] + 1u;   // one epoch per colour phase and neighbour, in both directions
+    counters[L.peer] = e;
+    st_release_sys(L.peer_flag, e);
+    wait_flag(L.my_flag, e, err, timeout_ns);
   }
 }
 
@@ -428,6 +425,14 @@ int Comm::connect(const HaloPlan &halo, int ncol_, cudaStream_t s) {
   const size_t send_total = (size_t) halo.send_total();
   if (send_total) CKC(cudaMalloc((void **) &send_dst, sizeof(int32_t) * send_total));
   std::vector<ConnectHead> heads((size_t) W);
+  // neighbouring ranks: any label traffic in either direction, in any colour (the same set on both sides, because
+  // the send list of one is the receive list of the other)
+  std::vector<char> is_nbr((size_t) W, 0);
+  for (int p = 0; p < W; p++)
+    for (int c = 0; c < ncol && p != rank; c++) {
+      const size_t e = (size_t) c * W + p;
+      if (halo.send_off[e + 1] > halo.send_off[e] || halo.recv_off[e + 1] > halo.recv_off[e]) is_nbr[(size_t) p] = 1;
+    }
   for (int p = 0; p < W; p++) {
     if (p == rank) continue;
     ConnectHead &ph = heads[(size_t) p];
@@ -449,7 +454,7 @@ int Comm::connect(const HaloPlan &halo, int ncol_, cudaStream_t s) {
       const int32_t r0 = poff[pe], r1 = poff[pe + 1];
       if (r1 - r0 != s1 - s0)
         return fail(BSB200_ERR_INVALID, "halo lists of ranks %d and %d disagree for colour %d (%d vs %d)", rank, p, c, s1 - s0, r1 - r0);
-      if (s1 == s0 && nrecv == 0) continue;
+      if (!is_nbr[(size_t) p]) continue;   // every colour phase of a neighbouring pair gets a leg, empty or not
       if (s1 > s0)
         CKC(cudaMemcpyAsync(send_dst + s0, reinterpret_cast<const int32_t *>(peer_arena[p] + ph.off_recv) + r0,
                             sizeof(int32_t) * (size_t) (s1 - s0), cudaMemcpyDefault, s));

@@ -232,6 +232,13 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
   };
   int kernels_per_iter = 0;
   param_kernel_init();
+  {   // the configuration must fit the shared memory of one CTA: say so instead of failing inside a launch
+    const size_t limit = device_smem_limit(), need = K.deconv_smem(deconv_args(-1, 1)), need_param = param_smem_min(q, d);
+    if (limit && (need > limit || need_param > std::min<size_t>(limit, 220 * 1024)))
+      return fail(BSB200_ERR_UNSUPPORTED,
+                  "d = %d, q = %d needs %zu (deconvolution sweep) / %zu (parameter update) bytes of shared memory per CTA, "
+                  "the device offers %zu: reduce q or d", d, q, need, need_param, limit);
+  }
   {   // statistics of the initial state
     DeconvArgs k = deconv_args(-1, 1);
     K.deconv(k, k.nseg, s);

@@ -296,12 +296,12 @@ size_t deconv_smem(const DeconvArgs &a) {
 void launch_deconv(const DeconvArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
   const size_t smem = deconv_smem(a);
-  static size_t attr0 = 0, attr1 = 0;
+  static size_t granted0[64] = {}, granted1[64] = {};
   if (a.adaptive) {
-    if (smem > attr1) { cudaFuncSetAttribute(k_deconv<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); attr1 = smem; }
+    if (ensure_dynamic_smem(k_deconv<D, true>, smem, granted1) != cudaSuccess) return;   // the launch check reports it
     k_deconv<D, true><<<grid, kBlock, smem, s>>>(a);
   } else {
-    if (smem > attr0) { cudaFuncSetAttribute(k_deconv<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); attr0 = smem; }
+    if (ensure_dynamic_smem(k_deconv<D, false>, smem, granted0) != cudaSuccess) return;
     k_deconv<D, false><<<grid, kBlock, smem, s>>>(a);
   }
 }

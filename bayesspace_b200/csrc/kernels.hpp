@@ -48,4 +48,21 @@ size_t sweep_smem_any(const KernelsForD &K, int tdist, int vvv, const SweepArgs 
 
 void launch_param(const ParamArgs &a, cudaStream_t stream);
 
+// Opts `kernel` into `bytes` of dynamic shared memory on the CURRENT device.  The attribute is per device (per
+// context), so the size already granted is remembered per device ordinal (`granted`: one static array per kernel
+// instantiation); a failure (more than the device offers) is returned to the caller instead of surfacing as an
+// 'invalid argument' of the launch.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&granted)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && bytes <= granted[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev] = bytes;
+  return e;
+}
+// Shared memory one CTA may use on the current device (opt-in maximum), 0 when it cannot be queried.
+size_t device_smem_limit();
+
 }   // namespace bsb

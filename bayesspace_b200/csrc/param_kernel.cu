@@ -428,6 +428,8 @@ static param_kernel_t *param_kernel_table() {
 #endif
 }
 
+size_t param_smem_min(int q, int d) { return (3 * (size_t) q * d + 4 * (size_t) d * d) * sizeof(double); }
+
 void launch_param(const ParamArgs &a, cudaStream_t stream) {
   const int d = a.PL.d, q = a.PL.q;
   const size_t per_mat = 4 * (size_t) d * d * sizeof(double);

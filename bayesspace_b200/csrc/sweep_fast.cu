@@ -483,14 +483,9 @@ template <bool TDIST, int NH>
 int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
   const FastSmem L = fast_smem_layout(D, a.PL.q, a.SL.E, TDIST, NH, a.maxdeg);
-  static size_t attr[64] = {};   // opted-in dynamic shared memory, per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || L.bytes > attr[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_fast<D, TDIST, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.bytes);
-    if (e != cudaSuccess) return (int) e;
-    if (dev >= 0 && dev < 64) attr[dev] = L.bytes;
-  }
+  static size_t granted[64] = {};
+  const cudaError_t e = ensure_dynamic_smem(k_sweep_fast<D, TDIST, NH>, L.bytes, granted);
+  if (e != cudaSuccess) return (int) e;
   k_sweep_fast<D, TDIST, NH><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
   return 0;
 }

@@ -262,11 +262,8 @@ template <bool TDIST, bool VVV>
 void launch_sweep_t(const SweepArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
   const SweepSmem L = sweep_smem_layout(D, a.PL.q, a.PL.nl, D * (D + 1) / 2, a.SL.E, TDIST, VVV, a.SL.nlT > 1, a.maxdeg);
-  static size_t attr = 0;
-  if (L.bytes > attr) {
-    cudaFuncSetAttribute(k_sweep<D, TDIST, VVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.bytes);
-    attr = L.bytes;
-  }
+  static size_t granted[64] = {};
+  if (ensure_dynamic_smem(k_sweep<D, TDIST, VVV>, L.bytes, granted) != cudaSuccess) return;   // the launch check reports it
   k_sweep<D, TDIST, VVV><<<grid, kBlock, L.bytes, s>>>(a);
 }
 

@@ -22,16 +22,22 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     rank, W = dist.get_rank(), dist.get_world_size()
-    cases = [("small_sq", (64, 64), "iterate", 16), ("small_hex", (60, 40), "iterate_t", 64),
-             ("small_sq", (48, 64), "iterate_t_vvv", 8), ("small_hex", (40, 30), "iterate_vvv", 8)]
+    # last case: a proper FOUR-colouring of the square lattice, (row % 2) * 2 + col % 2 -- the boundary row of a strip
+    # then holds only two of the four colours, so every colour phase has label traffic in ONE direction only between
+    # two neighbouring ranks (the one-sided legs the symmetric handshake of the peer transport exists for)
+    cases = [("small_sq", (64, 64), "iterate", 16, None), ("small_hex", (60, 40), "iterate_t", 64, None),
+             ("small_sq", (48, 64), "iterate_t_vvv", 8, None), ("small_hex", (40, 30), "iterate_vvv", 8, None),
+             ("small_sq", (64, 48), "iterate_t", 16, "four")]
     transports = os.environ.get("BSB200_CHECK_TRANSPORTS", "peer,nccl").split(",")
-    for name, shape, fname, groups in [c for c in cases for _ in transports]:
+    for name, shape, fname, groups, colouring in [c for c in cases for _ in transports]:
         transport = transports[0]
         transports = transports[1:] + transports[:1]
         os.environ["BSB200_COMM"] = transport   # read when the id is made: peer-memory stores (default) or NCCL
         w = synth.make_workload(name, n_override=shape)
         _, csr = B.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
         colour = B.colour_lattice(w.array_row, w.array_col, w.platform)
+        if colouring == "four":
+            colour = (((w.array_row % 2) * 2 + w.array_col % 2).astype(np.int32), 4)
         args = (w.Y, csr, 24, 4, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0, w.alpha, w.beta)
         f = getattr(B, fname)
         ids = [samplers.comm_unique_id() if rank == 0 else None]   # one communicator id per sharded chain

@@ -165,3 +165,14 @@ def test_deconv_parity_over_q(bsb, oracle, q):
     assert np.allclose(got["mu"], ref["mu"], rtol=1e-8, atol=1e-8)
     assert np.allclose(got["Y"], ref["Y"], rtol=1e-8, atol=1e-8)
     assert np.array_equal(got["Ychange"][1:], ref["Ychange"][1:])
+
+
+def test_configuration_beyond_shared_memory_is_reported(bsb):
+    """d = 32 with q = 255 clusters and per-cluster precisions needs far more shared memory than one CTA has:
+    the library says so (BSB200_ERR_UNSUPPORTED) instead of failing inside a launch."""
+    w = _square_workload(40, 40, 32, 2, seed=9)
+    _, csr, colour, _ = _graph(bsb, w)
+    init = (np.arange(w.n) % 255 + 1).astype(np.int32)
+    with pytest.raises(bsb.BayesSpaceError, match="shared memory") as ei:
+        bsb.iterate_t_vvv(w.Y, csr, 4, 1, w.n, w.d, w.gamma, 255, init, w.mu0, w.lambda0, w.alpha, w.beta, colour=colour)
+    assert ei.value.code == -7
