@@ -717,10 +717,12 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
       }
       int rc = check_device_error(ch);
       if (rc) return rc;
-      if (honour_cancel && g_cancel.load()) {   // early_stop at a thin boundary (src/cluster.cpp:1106)
-        if (device_ms) *device_ms = total_ms;
-        return fail(BSB200_ERR_CANCELLED, "Stopping...");
-      }
+    }
+    // early_stop at a thin boundary (src/cluster.cpp:1106) / user interrupt (checkUserInterrupt, :243-244): polled
+    // after every batch of at most `thin` iterations
+    if (honour_cancel && cancel_requested()) {
+      if (device_ms) *device_ms = total_ms;
+      return fail(BSB200_ERR_CANCELLED, "Stopping...");
     }
   }
   if (device_ms) *device_ms = total_ms;

@@ -14,6 +14,10 @@ namespace bsb {
 extern thread_local std::string g_last_error;
 extern std::atomic<int> g_cancel;
 extern std::atomic<long long> g_launches;
+extern bsb200_poll_fn g_poll;
+extern void *g_poll_user;
+// bsb200_cancel() seen, or the registered interrupt poll asks to stop (include/bsb200.h)
+bool cancel_requested();
 
 // Records the message bsb200_last_error() returns and hands back `code`.
 int fail(int code, const char *fmt, ...);

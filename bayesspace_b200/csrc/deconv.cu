@@ -323,8 +323,9 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
       int e = 0;
       CK(cudaMemcpy(&e, err.p, sizeof(int), cudaMemcpyDeviceToHost));
       if (e) return fail(BSB200_ERR_NUMERIC, "NA in probability vector, Wishart df <= 0 or matrix not positive definite");
-      if (g_cancel.load()) { status = fail(BSB200_ERR_CANCELLED, "Stopping..."); break; }
     }
+    // early stop (:1106-1107) / user interrupt (:867-868), polled after every batch of at most `thin` iterations
+    if (cancel_requested()) { status = fail(BSB200_ERR_CANCELLED, "Stopping..."); break; }
   }
   {
     int e = 0;

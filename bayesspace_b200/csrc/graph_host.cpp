@@ -19,6 +19,12 @@ namespace bsb {
 
 thread_local std::string g_last_error;
 std::atomic<int> g_cancel{0};
+bsb200_poll_fn g_poll = nullptr;
+void *g_poll_user = nullptr;
+bool cancel_requested() {
+  if (g_poll && g_poll(g_poll_user) != 0) g_cancel.store(1);
+  return g_cancel.load() != 0;
+}
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -292,6 +298,10 @@ extern "C" {
 int bsb200_version(void) { return BSB200_VERSION; }
 const char *bsb200_last_error(void) { return g_last_error.c_str(); }
 void bsb200_cancel(void) { g_cancel.store(1); }
+void bsb200_set_interrupt_poll(bsb200_poll_fn poll, void *user) {
+  bsb::g_poll_user = user;
+  bsb::g_poll = poll;
+}
 
 int bsb200_neighbors_lattice(const int32_t *array_row, const int32_t *array_col, int64_t n,
                              int32_t platform, int64_t *ptr, int32_t *idx, int64_t cap, int64_t *nnz) {

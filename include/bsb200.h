@@ -56,6 +56,13 @@ const char *bsb200_last_error(void);
 /* SIGTERM analogue (src/cluster.cpp:41-47, :1106-1107): running samplers stop at the next thin
  * boundary.  The flag is cleared when a sampler call starts. */
 void bsb200_cancel(void);
+/* User interrupts (Rcpp::checkUserInterrupt() every 10 iterations, src/cluster.cpp:243-244, :356-357, :475-476,
+ * :606-607, :867-868): the host registers a poll function; every sampler call invokes it on the calling thread
+ * after each batch of at most `thin` iterations, and a non-zero return stops the call like bsb200_cancel()
+ * (BSB200_ERR_CANCELLED; rows_done tells which snapshot rows are complete).  The function must return, not
+ * longjmp / throw (the R shim wraps R_CheckUserInterrupt in R_ToplevelExec).  NULL unregisters. */
+typedef int (*bsb200_poll_fn)(void *user);
+void bsb200_set_interrupt_poll(bsb200_poll_fn poll, void *user);
 int bsb200_device_count(void);
 
 /* ------------------------------------------------------------------------------------------------

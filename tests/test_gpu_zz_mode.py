@@ -57,3 +57,33 @@ def test_deconv_label_mode_and_mean(bsb, oracle):
     got = bsb.iterate_deconv(*args, seed=8, mean_from=3, mode_from=3)
     assert np.array_equal(got["z_mode"], oracle.mode_rows(got["z"][3:]))
     assert np.allclose(got["Y_mean"], got["Y"][3:].mean(axis=0), rtol=1e-12, atol=1e-12)
+
+
+def test_interrupt_poll_stops_the_call(bsb):
+    """Rcpp::checkUserInterrupt() analogue (src/cluster.cpp:243-244): the host registers a poll function, the library
+    calls it after every batch of at most `thin` iterations, and a non-zero return ends the call with
+    BSB200_ERR_CANCELLED ("Stopping..."), the snapshot rows reached so far being complete."""
+    import ctypes as C
+    from bayesspace_b200 import _lib, synth
+    w = synth.make_workload("small_hex")
+    _, csr = bsb.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
+    calls = []
+    POLL = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+    def poll(_user):
+        calls.append(1)
+        return 1 if len(calls) >= 3 else 0
+
+    cb = POLL(poll)
+    L = _lib.lib()
+    L.bsb200_set_interrupt_poll.argtypes = [POLL, C.c_void_p]
+    L.bsb200_set_interrupt_poll.restype = None
+    L.bsb200_set_interrupt_poll(cb, None)
+    try:
+        with pytest.raises(bsb.BayesSpaceError, match="Stopping") as ei:
+            bsb.iterate_t(w.Y, csr, 1000, 10, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0, w.alpha, w.beta, seed=4)
+        assert ei.value.code == -8 and len(calls) == 3
+    finally:
+        L.bsb200_set_interrupt_poll(POLL(0), None)
+    out = bsb.iterate_t(w.Y, csr, 40, 10, w.n, w.d, w.gamma, w.q, w.init, w.mu0, w.lambda0, w.alpha, w.beta, seed=4)
+    assert out["_info"]["rows_done"] == 5          # the poll is gone: the next call runs to the end
