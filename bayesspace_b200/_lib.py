@@ -63,7 +63,7 @@ class DeconvOut(C.Structure):
 
 # every symbol include/bsb200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "bsb200_version", "bsb200_last_error", "bsb200_cancel", "bsb200_device_count",
+    "bsb200_version", "bsb200_last_error", "bsb200_cancel", "bsb200_set_interrupt_poll", "bsb200_device_count",
     "bsb200_neighbors_lattice", "bsb200_neighbors_radius", "bsb200_parse_neighbor_strings",
     "bsb200_subspot_neighbors", "bsb200_neighbors_to_matrix4", "bsb200_colour_graph", "bsb200_colour_lattice",
     "bsb200_cluster", "bsb200_comm_unique_id", "bsb200_shard_plan", "bsb200_chain_create", "bsb200_chain_run", "bsb200_chain_profile", "bsb200_chain_state",
