@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <string>
+#include <thread>
 
 #include "comm.hpp"
 #include "shard.hpp"
@@ -146,17 +148,31 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
   const size_t nb = (size_t) ngroups * ncol;
   std::vector<int64_t> cnt(nb, 0), start(nb + 1, 0);
   auto grp = [&](int64_t j) { return (int) ((j * (int64_t) ngroups_total) / n) - g0; };
-  for (int64_t j = lo; j < hi; j++) cnt[(size_t) grp(j) * ncol + colour[j]]++;
+  // counting sort by (group, colour), stable in the original id; chunks of spots counted and placed by host threads
+  const int nchunk = parallel_chunks(n_own);
+  std::vector<std::vector<int64_t>> ccnt((size_t) nchunk, std::vector<int64_t>(nb, 0));
+  parallel_for(n_own, [&](int64_t a, int64_t b, int t) {
+    std::vector<int64_t> &c = ccnt[(size_t) t];
+    for (int64_t j = lo + a; j < lo + b; j++) c[(size_t) grp(j) * ncol + colour[j]]++;
+  });
+  for (size_t b = 0; b < nb; b++)
+    for (int t = 0; t < nchunk; t++) cnt[b] += ccnt[(size_t) t][b];
   for (size_t b = 0; b < nb; b++) start[b + 1] = (start[b] + cnt[b] + align - 1) / align * align;
   npos = nb ? start[nb - 1] + cnt[nb - 1] : 0;
   perm.assign((size_t) npos, -1);
   inv.resize((size_t) n_own);
-  std::vector<int64_t> fill(start.begin(), start.end() - 1);
-  for (int64_t j = lo; j < hi; j++) {
-    const int64_t pos = fill[(size_t) grp(j) * ncol + colour[j]]++;
-    perm[(size_t) pos] = (int32_t) j;
-    inv[(size_t) (j - lo)] = (int32_t) pos;
+  for (size_t b = 0; b < nb; b++) {   // first position of chunk t inside bucket b
+    int64_t at = start[b];
+    for (int t = 0; t < nchunk; t++) { const int64_t c = ccnt[(size_t) t][b]; ccnt[(size_t) t][b] = at; at += c; }
   }
+  parallel_for(n_own, [&](int64_t a, int64_t b, int t) {
+    std::vector<int64_t> &fill = ccnt[(size_t) t];
+    for (int64_t j = lo + a; j < lo + b; j++) {
+      const int64_t pos = fill[(size_t) grp(j) * ncol + colour[j]]++;
+      perm[(size_t) pos] = (int32_t) j;
+      inv[(size_t) (j - lo)] = (int32_t) pos;
+    }
+  });
   seg_begin.clear(); seg_count.clear(); seg_slot.clear();
   colour_seg_start.assign((size_t) ncol + 1, 0);
   group_start.assign((size_t) ngroups + 1, 0);
@@ -357,12 +373,29 @@ static int validate(const bsb200_cluster_args *a) {
   if (!a->Y || !a->nbr_ptr || !a->init || !a->mu0 || !a->lambda0) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
   if (a->model != BSB200_MODEL_NORMAL && a->model != BSB200_MODEL_T) return fail(BSB200_ERR_INVALID, "unknown model %d", a->model);
   if (a->precision != BSB200_PRECISION_EQUAL && a->precision != BSB200_PRECISION_VARIABLE) return fail(BSB200_ERR_INVALID, "unknown precision %d", a->precision);
-  for (int64_t j = 0; j < a->n; j++) {
-    if (a->init[j] < 1 || a->init[j] > a->q) return fail(BSB200_ERR_INVALID, "init[%lld] = %d outside 1..q", (long long) j, a->init[j]);
-    const int64_t dg = a->nbr_ptr[j + 1] - a->nbr_ptr[j];
-    if (dg < 0 || dg > kMaxDeg) return fail(BSB200_ERR_UNSUPPORTED, "spot %lld has %lld neighbours (max %d)", (long long) j, (long long) dg, kMaxDeg);
-    for (int64_t e = a->nbr_ptr[j]; e < a->nbr_ptr[j + 1]; e++)
-      if (a->nbr_idx[e] < 0 || a->nbr_idx[e] >= a->n) return fail(BSB200_ERR_INVALID, "neighbour index out of range at spot %lld", (long long) j);
+  // the first offending spot (lowest id) is reported, whichever host thread finds it
+  std::vector<int64_t> first_bad((size_t) parallel_chunks(a->n), -1);
+  std::vector<int> first_kind(first_bad.size(), 0);
+  parallel_for(a->n, [&](int64_t lo, int64_t hi, int t) {
+    for (int64_t j = lo; j < hi; j++) {
+      int kind = 0;
+      const int64_t dg = a->nbr_ptr[j + 1] - a->nbr_ptr[j];
+      if (a->init[j] < 1 || a->init[j] > a->q) kind = 1;
+      else if (dg < 0 || dg > kMaxDeg) kind = 2;
+      else
+        for (int64_t e = a->nbr_ptr[j]; e < a->nbr_ptr[j + 1]; e++)
+          if (a->nbr_idx[e] < 0 || a->nbr_idx[e] >= a->n) { kind = 3; break; }
+      if (kind) { first_bad[(size_t) t] = j; first_kind[(size_t) t] = kind; return; }
+    }
+  });
+  for (size_t t = 0; t < first_bad.size(); t++) {
+    const int64_t j = first_bad[t];
+    if (j < 0) continue;
+    if (first_kind[t] == 1) return fail(BSB200_ERR_INVALID, "init[%lld] = %d outside 1..q", (long long) j, a->init[j]);
+    if (first_kind[t] == 2)
+      return fail(BSB200_ERR_UNSUPPORTED, "spot %lld has %lld neighbours (max %d)", (long long) j,
+                  (long long) (a->nbr_ptr[j + 1] - a->nbr_ptr[j]), kMaxDeg);
+    return fail(BSB200_ERR_INVALID, "neighbour index out of range at spot %lld", (long long) j);
   }
   return BSB200_OK;
 }
@@ -441,6 +474,35 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   const ShardPlan &plan = ch->plan;
   ch->G = G; ch->lo = plan.lo; ch->hi = plan.hi; ch->n_own = plan.n_own();
   const int64_t n_own = ch->n_own;
+  // The PCs are the bulk of the input (1.2 GB at 10M spots): their upload runs on a second host thread while this one
+  // colours, orders and stages the graph.  Own rows of Y (R's column-major n x d): one strided copy.
+  DevBuf<double> Yraw;
+  struct Uploader {
+    std::thread th;
+    int rc = BSB200_OK;
+    std::string msg;
+    ~Uploader() { if (th.joinable()) th.join(); }
+  } yup;
+  struct Pinner {   // page-locked snapshot staging (120 MB at 10M spots), allocated off the critical path
+    std::thread th;
+    cudaError_t e = cudaSuccess;
+    ~Pinner() { if (th.joinable()) th.join(); }
+  } pin;
+  pin.th = std::thread([&, device = a->device, chp = ch.get()]() {
+    pin.e = cudaSetDevice(device);
+    if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_z, sizeof(int32_t) * std::max<int64_t>(n_own, 1));
+    if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_w, sizeof(double) * std::max<int64_t>(n_own, 1));
+  });
+  yup.th = std::thread([&, device = a->device]() {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&Yraw.p, sizeof(double) * std::max<size_t>((size_t) n_own * d, 1));
+    if (e == cudaSuccess) {
+      Yraw.count = (size_t) n_own * d;
+      e = cudaMemcpy2D(Yraw.p, sizeof(double) * n_own, a->Y + plan.lo, sizeof(double) * n, sizeof(double) * n_own, (size_t) d,
+                       cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) { yup.rc = BSB200_ERR_CUDA; yup.msg = cudaGetErrorString(e); }
+  });
 
   // ---- colouring (of the whole graph: every rank derives the same classes) ------------------------
   std::vector<int32_t> colour;
@@ -489,32 +551,52 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     ch->recv_pos.adopt(ch->comm.recv_pos(), ch->halo.recv_pos.size());
   }
   int maxdeg = 0;
-  for (int64_t j = 0; j < n; j++) maxdeg = std::max<int>(maxdeg, (int) (a->nbr_ptr[j + 1] - a->nbr_ptr[j]));
+  {
+    std::vector<int> md((size_t) parallel_chunks(n), 0);
+    parallel_for(n, [&](int64_t lo, int64_t hi, int t) {
+      int m = 0;
+      for (int64_t j = lo; j < hi; j++) m = std::max<int>(m, (int) (a->nbr_ptr[j + 1] - a->nbr_ptr[j]));
+      md[(size_t) t] = m;
+    });
+    for (int m : md) maxdeg = std::max(maxdeg, m);
+  }
   ch->maxdeg = maxdeg;
   {
-    std::vector<int32_t> ell((size_t) std::max(maxdeg, 1) * ch->ld + kSweepPad, -1);
-    std::vector<uint8_t> z0((size_t) ch->ld, 0);
-    for (int64_t i = 0; i < n_pos; i++) {
-      const int64_t j = ord.perm[(size_t) i];
-      if (j < 0) continue;   // hole
-      z0[(size_t) i] = (uint8_t) (a->init[j] - 1);
-      int e = 0;
-      for (int64_t p = a->nbr_ptr[j]; p < a->nbr_ptr[j + 1]; p++, e++) {
-        const int32_t u = a->nbr_idx[p];
-        int32_t pos;
-        if (u >= plan.lo && u < plan.hi) pos = ord.inv[(size_t) (u - plan.lo)];
-        else pos = (int32_t) (n_pos + (std::lower_bound(plan.ghosts.begin(), plan.ghosts.end(), u) - plan.ghosts.begin()));
-        ell[(size_t) e * ch->ld + i] = pos;
+    // neighbour ids in internal order (ELL, -1 padded), initial labels and original ids, filled by host threads
+    const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;
+    std::unique_ptr<int32_t[]> ell(new int32_t[ell_rows * ldp + kSweepPad]);
+    std::unique_ptr<uint8_t[]> z0(new uint8_t[ldp]);
+    std::unique_ptr<int32_t[]> origp(new int32_t[ldp + kSweepPad]);
+    parallel_for((int64_t) ldp, [&](int64_t i0, int64_t i1, int) {
+      for (int64_t i = i0; i < i1; i++) {
+        const int64_t j = i < n_pos ? (int64_t) ord.perm[(size_t) i] : (int64_t) -1;
+        int e = 0;
+        if (j >= 0) {
+          z0[(size_t) i] = (uint8_t) (a->init[j] - 1);
+          origp[(size_t) i] = (int32_t) j;
+          for (int64_t p = a->nbr_ptr[j]; p < a->nbr_ptr[j + 1]; p++, e++) {
+            const int32_t u = a->nbr_idx[p];
+            int32_t pos;
+            if (u >= plan.lo && u < plan.hi) pos = ord.inv[(size_t) (u - plan.lo)];
+            else pos = (int32_t) (n_pos + (std::lower_bound(plan.ghosts.begin(), plan.ghosts.end(), u) - plan.ghosts.begin()));
+            ell[(size_t) e * ldp + (size_t) i] = pos;
+          }
+        } else {   // hole of the internal order, ghost or padding
+          z0[(size_t) i] = 0;
+          origp[(size_t) i] = -1;
+        }
+        for (; e < (int) ell_rows; e++) ell[(size_t) e * ldp + (size_t) i] = -1;
       }
+    });
+    for (size_t e = 0; e < (size_t) kSweepPad; e++) { ell[ell_rows * ldp + e] = -1; origp[ldp + e] = -1; }
+    for (size_t gi = 0; gi < plan.ghosts.size(); gi++) {
+      z0[(size_t) n_pos + gi] = (uint8_t) (a->init[plan.ghosts[gi]] - 1);
+      origp[(size_t) n_pos + gi] = plan.ghosts[gi];
     }
-    for (size_t gi = 0; gi < plan.ghosts.size(); gi++) z0[(size_t) n_pos + gi] = (uint8_t) (a->init[plan.ghosts[gi]] - 1);
-    if ((rc = upload(ch->ell, ell.data(), ell.size(), s))) return rc;
-    if (ch->comm.peer()) CK(cudaMemcpyAsync(ch->z.p, z0.data(), z0.size(), cudaMemcpyHostToDevice, s));
-    else if ((rc = upload(ch->z, z0.data(), z0.size(), s))) return rc;
-    std::vector<int32_t> origp((size_t) ch->ld + kSweepPad, -1);
-    std::copy(ord.perm.begin(), ord.perm.end(), origp.begin());
-    std::copy(plan.ghosts.begin(), plan.ghosts.end(), origp.begin() + n_pos);
-    if ((rc = upload(ch->orig, origp.data(), origp.size(), s))) return rc;
+    if ((rc = upload(ch->ell, ell.get(), ell_rows * ldp + kSweepPad, s))) return rc;
+    if (ch->comm.peer()) CK(cudaMemcpyAsync(ch->z.p, z0.get(), ldp, cudaMemcpyHostToDevice, s));
+    else if ((rc = upload(ch->z, z0.get(), ldp, s))) return rc;
+    if ((rc = upload(ch->orig, origp.get(), ldp + kSweepPad, s))) return rc;
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }
   mark("ELL/z/orig staging");
@@ -537,14 +619,13 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
       return rc;
   }
   {
-    // own rows of Y (R's column-major n x d): one strided copy; column means from per-shard sums
-    DevBuf<double> Yraw, gcol;
+    // column means from per-shard sums (the upload of Y itself was started above)
+    DevBuf<double> gcol;
     DevBuf<int64_t> glo;
-    if ((rc = Yraw.alloc((size_t) n_own * d)) || (rc = gcol.alloc((size_t) G * d)) || (rc = ch->ybar.alloc((size_t) d)) ||
-        (rc = ch->Y.alloc((size_t) d * ch->ld + kSweepPad)))
+    if ((rc = gcol.alloc((size_t) G * d)) || (rc = ch->ybar.alloc((size_t) d)) || (rc = ch->Y.alloc((size_t) d * ch->ld + kSweepPad)))
       return rc;
-    CK(cudaMemcpy2DAsync(Yraw.p, sizeof(double) * n_own, a->Y + plan.lo, sizeof(double) * n, sizeof(double) * n_own, (size_t) d,
-                         cudaMemcpyHostToDevice, s));
+    yup.th.join();
+    if (yup.rc) return fail(BSB200_ERR_CUDA, "upload of Y failed: %s", yup.msg.c_str());
     if ((rc = upload(glo, plan.group_lo.data(), plan.group_lo.size(), s))) return rc;
     CK(cudaMemsetAsync(ch->Y.p, 0, sizeof(double) * ((size_t) d * ch->ld + kSweepPad), s));
     CK(cudaMemsetAsync(gcol.p, 0, sizeof(double) * G * d, s));
@@ -570,8 +651,8 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   }
   mark("Y upload+centre");
   {
-    std::vector<double> w1((size_t) ch->ld, 1.0);
-    if ((rc = upload(ch->w, w1.data(), w1.size(), s))) return rc;
+    if ((rc = ch->w.alloc((size_t) ch->ld))) return rc;
+    launch_fill_f64(ch->w.p, ch->ld, 1.0, s);
     std::vector<double> mu0c((size_t) d), lm0((size_t) d, 0.0);
     for (int c = 0; c < d; c++) mu0c[(size_t) c] = a->mu0[c] - ch->ybar_host[(size_t) c];
     for (int i = 0; i < d; i++)
@@ -616,8 +697,8 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     CK(cudaMemcpyAsync(ch->plogLik.p, nanv.data(), sizeof(double) * a->nrep, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
   }
-  CK(cudaMallocHost(&ch->h_snap_z, sizeof(int32_t) * std::max<int64_t>(n_own, 1)));
-  CK(cudaMallocHost(&ch->h_snap_w, sizeof(double) * std::max<int64_t>(n_own, 1)));
+  pin.th.join();
+  if (pin.e != cudaSuccess) return fail(BSB200_ERR_CUDA, "pinned snapshot staging: %s", cudaGetErrorString(pin.e));
 
   {
     const char *msg = "";
@@ -670,6 +751,17 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
   cudaStream_t s = ch->stream;
   double total_ms = 0.0;
   int64_t remaining = iters;
+  // A snapshot staged in pinned memory is copied into the caller's matrices while the GPU already runs the next batch
+  // (the copy touches fresh pages of a 1.3 GB allocation at 10M spots: ~30 ms per row that used to idle the GPU).
+  int64_t pending_row = -1;
+  auto flush_pending = [&]() {
+    if (pending_row < 0) return;
+    const size_t r = (size_t) pending_row;
+    if (out->z) std::memcpy(out->z + r * ch->n + ch->lo, ch->h_snap_z, sizeof(int32_t) * ch->n_own);
+    if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n + ch->lo, ch->h_snap_w, sizeof(double) * ch->n_own);
+    out->rows_done = (int32_t) r + 1;
+    pending_row = -1;
+  };
   while (remaining > 0) {
     const int64_t it0 = ch->iters_done;   // iterations completed; next iteration index = it0 + 1
     const int64_t next_multiple = ((it0 + 2 + ch->thin - 1) / ch->thin) * ch->thin;
@@ -684,6 +776,7 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     g_launches += (long long) ch->kernels_per_iter * run;
     ch->iters_done += run;
     remaining -= run;
+    flush_pending();   // host copy of the previous snapshot, overlapped with the batch just enqueued
     const bool boundary = (ch->iters_done + 1) % ch->thin == 0;
     if (boundary) {
       const int64_t row = (ch->iters_done + 1) / ch->thin;
@@ -710,21 +803,19 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     total_ms += ms;
     if (boundary) {
       const size_t r = (size_t) ((ch->iters_done + 1) / ch->thin);
-      if (out && r < (size_t) (ch->nrep / ch->thin + 1)) {
-        if (out->z) std::memcpy(out->z + r * ch->n + ch->lo, ch->h_snap_z, sizeof(int32_t) * ch->n_own);
-        if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n + ch->lo, ch->h_snap_w, sizeof(double) * ch->n_own);
-        out->rows_done = (int32_t) r + 1;
-      }
+      if (out && r < (size_t) (ch->nrep / ch->thin + 1)) pending_row = (int64_t) r;
       int rc = check_device_error(ch);
-      if (rc) return rc;
+      if (rc) { flush_pending(); return rc; }
     }
     // early_stop at a thin boundary (src/cluster.cpp:1106) / user interrupt (checkUserInterrupt, :243-244): polled
     // after every batch of at most `thin` iterations
     if (honour_cancel && cancel_requested()) {
+      flush_pending();
       if (device_ms) *device_ms = total_ms;
       return fail(BSB200_ERR_CANCELLED, "Stopping...");
     }
   }
+  flush_pending();
   if (device_ms) *device_ms = total_ms;
   return check_device_error(ch);
 }

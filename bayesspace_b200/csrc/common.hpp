@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace bsb {
@@ -32,5 +33,25 @@ int subspot_neighbors(const double *pos, int64_t n, int64_t n0, const int64_t *s
 int colour_graph(const int64_t *ptr, const int32_t *idx, int64_t n, std::vector<int32_t> &colour,
                  int32_t *ncolours);
 bool colouring_is_proper(const int64_t *ptr, const int32_t *idx, int64_t n, const int32_t *colour);
+
+// Host threads for the O(n) set-up loops (validation, ordering, ELL staging): chunks [lo, hi) of [0, n) run on up to
+// BSB200_HOST_THREADS (default: min(hardware threads, 16)) threads; small n runs inline.  fn must be thread-safe.
+int host_threads();
+template <typename F>
+inline void parallel_for(int64_t n, F fn, int64_t min_chunk = 1 << 18) {
+  int nt = host_threads();
+  if ((int64_t) nt > n / min_chunk) nt = (int) (n / min_chunk);
+  if (nt <= 1) { fn((int64_t) 0, n, 0); return; }
+  std::vector<std::thread> th;
+  th.reserve((size_t) nt - 1);
+  for (int t = 1; t < nt; t++) th.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt, t); });
+  fn((int64_t) 0, n / nt, 0);
+  for (auto &x : th) x.join();
+}
+inline int parallel_chunks(int64_t n, int64_t min_chunk = 1 << 18) {   // number of chunks parallel_for will use
+  int nt = host_threads();
+  if ((int64_t) nt > n / min_chunk) nt = (int) (n / min_chunk);
+  return nt < 1 ? 1 : nt;
+}
 
 }   // namespace bsb

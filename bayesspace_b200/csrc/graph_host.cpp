@@ -10,6 +10,7 @@
 #include "common.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <unordered_map>
@@ -282,11 +283,23 @@ int colour_graph(const int64_t *ptr, const int32_t *idx, int64_t n, std::vector<
 }
 
 // true when no directed edge joins two spots of one colour (self loops excepted)
+int host_threads() {
+  static const int nt = []() {
+    int v = (int) std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("BSB200_HOST_THREADS")) v = std::atoi(e);
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+  }();
+  return nt;
+}
+
 bool colouring_is_proper(const int64_t *ptr, const int32_t *idx, int64_t n, const int32_t *colour) {
-  for (int64_t i = 0; i < n; i++)
-    for (int64_t e = ptr[i]; e < ptr[i + 1]; e++)
-      if (idx[e] != i && colour[idx[e]] == colour[i]) return false;
-  return true;
+  std::atomic<int> bad{0};
+  parallel_for(n, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t i = lo; i < hi && !bad.load(std::memory_order_relaxed); i++)
+      for (int64_t e = ptr[i]; e < ptr[i + 1]; e++)
+        if (idx[e] != i && colour[idx[e]] == colour[i]) { bad.store(1); return; }
+  });
+  return bad.load() == 0;
 }
 
 }   // namespace bsb

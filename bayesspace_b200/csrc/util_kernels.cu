@@ -223,6 +223,15 @@ void launch_permute_center(const double *Y, int64_t src_ld, int64_t count, int d
   k_permute_center<<<(unsigned) ((count + 255) / 256), 256, 0, s>>>(Y, src_ld, count, d, orig, ybar, Yp, dst_ld, orig_off);
   g_launches++;
 }
+__global__ void k_fill_f64(double *p, int64_t n, double v) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+void launch_fill_f64(double *p, int64_t n, double v, cudaStream_t s) {
+  if (n <= 0) return;
+  k_fill_f64<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(p, n, v);
+  g_launches++;
+}
 void launch_snapshot(const uint8_t *z, const double *w, const int32_t *orig, int64_t n, int32_t *z_out,
                      double *w_out, cudaStream_t s, int64_t orig_off) {
   k_snapshot<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(z, w, orig, n, z_out, w_out, orig_off);

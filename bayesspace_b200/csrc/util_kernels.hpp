@@ -8,6 +8,7 @@
 
 namespace bsb {
 extern std::atomic<long long> g_launches;
+void launch_fill_f64(double *p, int64_t n, double v, cudaStream_t s);
 void launch_colmeans(const double *Y, int64_t n, int d, double *ybar, cudaStream_t s);
 void launch_permute_center(const double *Y, int64_t src_ld, int64_t count, int d, const int32_t *orig,
                            const double *ybar, double *Yp, int64_t dst_ld, cudaStream_t s, int64_t orig_off = 0);
