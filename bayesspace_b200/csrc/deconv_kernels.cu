@@ -230,22 +230,66 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           hp_move = -0.5 * wj * lin_n;   // ... if it moves (:1035, :1048)
         }
         // ---- sequential label updates inside each parent: r = 0..S-1, neighbour labels live (:984,:1029-1051)
-        for (int turn = 0; turn < S; turn++) {
-          if (active && r == turn) {
-            int deg = 0, cp = 0, cn = 0;
-            for (int ee = 0; ee < a.maxdeg; ee++) {
-              const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
-              if (nb >= 0) {
-                deg++;
-                const int zu = *((volatile uint8_t *) (a.z + nb));
-                cp += (zu == zk);
-                cn += (zu == zn);
-              }
+        // Neighbours in OTHER parents belong to another colour class and do not change during this launch: their
+        // labels are gathered once, before the turns.  Neighbours inside the parent sit on adjacent lanes: their live
+        // label is the lane's register, fetched by shuffle at every turn -- no memory traffic inside the scan.
+        constexpr int kNbReg = 8;
+        int zu[kNbReg], src[kNbReg];
+        int deg = 0;
+#pragma unroll
+        for (int ee = 0; ee < kNbReg; ee++) {
+          zu[ee] = -1;
+          src[ee] = lane;
+          if (active && ee < a.maxdeg) {
+            const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
+            if (nb >= 0) {
+              deg++;
+              const int32_t rr = nb / (int32_t) a.ld0, ipn = nb - rr * (int32_t) a.ld0;
+              if (ipn == (int32_t) ip) src[ee] = glane0 + rr;   // same parent: live label of that lane
+              else zu[ee] = a.z[nb];
             }
+          }
+        }
+        int deg_more = 0, cp_more = 0, cn_more = 0;   // neighbours beyond kNbReg (general graphs): other parents only counted here
+        bool more_same_parent = false;
+        if (active)
+          for (int ee = kNbReg; ee < a.maxdeg; ee++) {
+            const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
+            if (nb >= 0) {
+              const int32_t rr = nb / (int32_t) a.ld0, ipn = nb - rr * (int32_t) a.ld0;
+              if (ipn == (int32_t) ip) { more_same_parent = true; continue; }
+              deg_more++;
+              const int z2 = a.z[nb];
+              cp_more += z2 == zk;
+              cn_more += z2 == zn;
+            }
+          }
+        double pscale = 0.0;
+        for (int turn = 0; turn < S; turn++) {
+          int cp = cp_more, cn = cn_more, dg = deg + deg_more;
+#pragma unroll
+          for (int ee = 0; ee < kNbReg; ee++) {
+            const int live = __shfl_sync(0xffffffffu, zfinal, src[ee]);
+            const int zv = src[ee] != lane ? live : zu[ee];
+            cp += zv == zk;
+            cn += zv == zn;
+          }
+          if (active && r == turn) {
+            if (more_same_parent)   // more than kNbReg neighbours, some of them in the own parent: read those live
+              for (int ee = kNbReg; ee < a.maxdeg; ee++) {
+                const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
+                if (nb >= 0 && nb % (int32_t) a.ld0 == (int32_t) ip) {
+                  dg++;
+                  const int z2 = *((volatile uint8_t *) (a.z + nb));
+                  cp += z2 == zk;
+                  cn += z2 == zn;
+                }
+              }
             double pot_p = 0.0, pot_n = 0.0;
-            if (deg) {
-              pot_p = a.gamma / deg * 2 * cp;
-              pot_n = a.gamma / deg * 2 * cn;
+            if (dg) {
+              pscale = a.gamma / dg * 2;
+              pot_p = pscale * cp;
+              pot_n = pscale * cn;
             }
             const double prob = exp((pot_n - pot_p) + dl_z);
             if (prob != prob) atomicExch(a.err, BSB_DEVERR_NUMERIC);
@@ -257,7 +301,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
             } else {
               hp_acc += hp_stay;
             }
-            __threadfence_block();
+            if (more_same_parent) __threadfence_block();
           }
           __syncwarp();
         }
