@@ -159,6 +159,24 @@ def iterate_t_vvv(Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha
     return _run_cluster("t", "variable", Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta, **kw)
 
 
+def init_cluster(Y, q, init=None, init_method="mclust", seed=0, max_iter=0, device=0, return_centers=False):
+    """.init_cluster (R/spatialCluster.R:317-328): the given init, or labels 1..q from "kmeans" (k-means++ + Lloyd) /
+    "mclust" (shared-covariance Gaussian mixture, EM) computed on the device."""
+    if init is not None:
+        return np.asarray(init, dtype=np.int32)
+    if init_method not in ("mclust", "kmeans"):
+        raise ValueError("'arg' should be one of 'mclust', 'kmeans'")
+    Y = np.asarray(Y, dtype=np.float64)
+    n, d = Y.shape
+    out = np.zeros(n, dtype=np.int32)
+    cen = np.zeros((q, d))
+    it = C.c_int32(0)
+    yb = colmajor(Y)
+    check(lib().bsb200_init_cluster(device, ptr(yb), C.c_int64(n), d, q, 1 if init_method == "mclust" else 0,
+                                    C.c_uint64(seed), int(max_iter), ptr(out), ptr(cen), C.byref(it)))
+    return (out, cen, int(it.value)) if return_centers else out
+
+
 def cluster(Y, q, df_j, init=None, model="t", precision="equal", mu0=None, lambda0=None, gamma=3, alpha=1,
             beta=0.01, nrep=1000, thin=100, **kw):
     """cluster() (R/spatialCluster.R:70-112): picks the sampler by (model, precision)."""

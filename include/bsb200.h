@@ -236,6 +236,36 @@ int bsb200_debug_rng(int32_t device, int32_t kind, uint64_t seed, uint32_t purpo
                      double *out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Initial labels: .init_cluster (R/spatialCluster.R:317-328), the step before the samplers
+ * ---------------------------------------------------------------------------------------------- */
+enum { BSB200_INIT_KMEANS = 0, BSB200_INIT_MCLUST = 1 };
+/* init.method "kmeans": k-means++ seeding + Lloyd iterations; "mclust": EM of the Gaussian mixture with one shared
+ * covariance (mclust's "EEE" model) started from that partition; labels = argmax of the responsibilities.
+ * stats::kmeans / mclust::Mclust draw from R's RNG and use algorithms of their own, so their labels are not
+ * reproducible bit for bit; the contract kept is: n labels in 1..q, every label present, deterministic under `seed`
+ * (Philox key, as for the samplers).  Y: n x d col-major.  max_iter <= 0: 100.  centers (optional): q x d row-major.
+ * Runs on the device: at 10M spots this R step would otherwise dominate spatialCluster(). */
+int bsb200_init_cluster(int32_t device, const double *Y, int64_t n, int32_t d, int32_t q, int32_t method,
+                        uint64_t seed, int32_t max_iter, int32_t *init, double *centers, int32_t *iters_done);
+
+/* ------------------------------------------------------------------------------------------------
+ * Helpers of spatialEnhance's benchmarking code (src/compare_enhanced.cpp; R/spatialEnhance.R:570-585)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* map_subspot2ref (src/compare_enhanced.cpp:47-92): for every subspot the reference spot(s) at minimal squared
+ * Euclidean distance; exact ties are all reported, as "find(dists == min(dists))" does.  Coordinates are ns x k and
+ * nr x k col-major (k <= 8).  The reference returns a 3-column matrix with one row (i, j, min dist^2) per tie; here:
+ * row_ptr[ns + 1] offsets of subspot i's ties in ref_idx (ascending j), min_dist2[ns], *nrows = total rows.
+ * Two-pass sizing like the neighbour builders: ref_idx == NULL returns *nrows only. */
+int bsb200_map_subspot2ref(int32_t device, const double *subspot_coords, int64_t ns, const double *ref_coords,
+                           int64_t nr, int32_t k, int64_t *row_ptr, int32_t *ref_idx, int64_t cap, double *min_dist2,
+                           int64_t *nrows);
+
+/* compute_corr (src/compare_enhanced.cpp:94-132): cor[i] = Pearson correlation of row i of m1 and m2
+ * (both nrow x ncol col-major).  The reference's first output column is the row index i itself. */
+int bsb200_compute_corr(int32_t device, const double *m1, const double *m2, int64_t nrow, int64_t ncol, double *cor);
+
+/* ------------------------------------------------------------------------------------------------
  * iterate_deconv (src/cluster.cpp:742-1141; R/RcppExports.R:20-22)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct bsb200_deconv_args {

@@ -233,6 +233,36 @@ def scan_fixed(variant, Y, df_j, gamma, q, init, mu, lam, niter, seed=0, order=N
     return hist, wm
 
 
+def map_subspot2ref(subspot_coords, ref_coords):
+    """src/compare_enhanced.cpp:47-92 (single thread): rows (i, j, squared distance), all exact ties."""
+    s = np.asarray(subspot_coords, dtype=np.float64)
+    r = np.asarray(ref_coords, dtype=np.float64)
+    ns, k = s.shape
+    nr = r.shape[0]
+    cap = 4 * ns + 64
+    out = np.zeros((cap, 3))
+    f = lib().orc_map_subspot2ref
+    f.restype = C.c_int64
+    rows = f(_p(_colmajor(s), C.c_double), C.c_int64(ns), _p(_colmajor(r), C.c_double), C.c_int64(nr), k,
+             _p(out, C.c_double), C.c_int64(cap))
+    if rows < 0:
+        raise RuntimeError("too many ties")
+    return out[:rows].copy()
+
+
+def compute_corr(m1, m2):
+    """src/compare_enhanced.cpp:94-132: matrix (row index, Pearson correlation of the two rows)."""
+    a = np.asarray(m1, dtype=np.float64)
+    b = np.asarray(m2, dtype=np.float64)
+    if a.shape != b.shape:
+        raise RuntimeError("Input matrices should be of the same shape.")
+    n, p = a.shape
+    cor = np.zeros(n)
+    lib().orc_compute_corr(_p(_colmajor(a), C.c_double), _p(_colmajor(b), C.c_double), C.c_int64(n), C.c_int64(p),
+                           _p(cor, C.c_double))
+    return np.c_[np.arange(n, dtype=np.float64), cor]
+
+
 def _run_cluster(variant, Y, df_j, nrep, thin, n, d, gamma, q, init, mu0, lambda0, alpha, beta,
                  seed=0, order=None, compat=COMPAT_REFERENCE):
     Y = np.asarray(Y, dtype=np.float64)

@@ -1053,6 +1053,49 @@ int orc_scan_fixed(int variant, uint32_t compat, const double *Y, int64_t n, int
   return 0;
 }
 
+// map_subspot2ref (src/compare_enhanced.cpp:47-92): per subspot i the reference rows j with dists == min(dists),
+// dists = sum over columns of (sub[i, c] - ref[j, c])^2 in column order.  out: rows (i, j, min) appended in i order
+// (the reference's single-thread order); returns the number of rows, or -1 if cap is too small.
+int64_t orc_map_subspot2ref(const double *sub, int64_t ns, const double *ref, int64_t nr, int k, double *out, int64_t cap) {
+  int64_t rows = 0;
+  std::vector<double> dists((size_t) nr);
+  for (int64_t i = 0; i < ns; i++) {
+    double mn = std::numeric_limits<double>::infinity();
+    for (int64_t j = 0; j < nr; j++) {
+      double s = 0.0;
+      for (int c = 0; c < k; c++) {
+        const volatile double v = sub[(size_t) c * ns + i] - ref[(size_t) c * nr + j];
+        const volatile double v2 = v * v;   // separately rounded, as std::pow(v, 2) then arma::sum
+        s += v2;
+      }
+      dists[(size_t) j] = s;
+      if (s < mn) mn = s;
+    }
+    for (int64_t j = 0; j < nr; j++)
+      if (dists[(size_t) j] == mn) {
+        if (rows >= cap) return -1;
+        out[rows * 3] = (double) i; out[rows * 3 + 1] = (double) j; out[rows * 3 + 2] = mn;
+        rows++;
+      }
+  }
+  return rows;
+}
+
+// compute_corr (src/compare_enhanced.cpp:94-132): arma::cor of row i of m1 and of m2 (n x p col-major)
+void orc_compute_corr(const double *m1, const double *m2, int64_t n, int64_t p, double *cor) {
+  for (int64_t i = 0; i < n; i++) {
+    double ma = 0.0, mb = 0.0;
+    for (int64_t c = 0; c < p; c++) { ma += m1[(size_t) c * n + i]; mb += m2[(size_t) c * n + i]; }
+    ma /= (double) p; mb /= (double) p;
+    double sab = 0.0, saa = 0.0, sbb = 0.0;
+    for (int64_t c = 0; c < p; c++) {
+      const double a = m1[(size_t) c * n + i] - ma, b = m2[(size_t) c * n + i] - mb;
+      sab += a * b; saa += a * a; sbb += b * b;
+    }
+    cor[i] = sab / std::sqrt(saa * sbb);
+  }
+}
+
 int orc_iterate(int variant, const double *Y, int64_t n, int d, int q, const int64_t *nbr_ptr,
                 const int32_t *nbr_idx, int nrep, int thin, double gamma, const int32_t *init,
                 const double *mu0, const double *lambda0, double alpha, double beta, uint64_t seed,
