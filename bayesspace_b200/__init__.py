@@ -4,7 +4,8 @@ Only the path is here: the C ABI library (csrc/ -> libbsb200.so, include/bsb200.
 mirror of the reference's sampler interface (samplers.py), the neighbour construction behind it
 (neighbors.py) and the synthetic inputs used by tests and bench (synth.py).
 """
-from . import enhance_utils, neighbors, samplers, synth  # noqa: F401
+from . import chain_file as _chain_file, enhance_utils, neighbors, samplers, synth  # noqa: F401
+from .chain_file import chain_file, read_chain  # noqa: F401
 from .enhance_utils import compute_corr, map_subspot2ref  # noqa: F401
 from ._lib import COMPAT_Q1, COMPAT_Q3, COMPAT_REFERENCE, BayesSpaceError, device_count, kernel_launches  # noqa: F401
 from .neighbors import (colour_graph, colour_lattice, convert_neighbors, convert_neighbors2mtx,  # noqa: F401

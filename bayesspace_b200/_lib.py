@@ -69,7 +69,7 @@ EXPORTS = [
     "bsb200_cluster", "bsb200_comm_unique_id", "bsb200_shard_plan", "bsb200_chain_create", "bsb200_chain_run", "bsb200_chain_profile", "bsb200_chain_state",
     "bsb200_chain_destroy", "bsb200_kernel_launches", "bsb200_eval_loglik", "bsb200_eval_suffstats",
     "bsb200_chain_dry_sweep", "bsb200_debug_rng", "bsb200_debug_rendezvous", "bsb200_deconv",
-    "bsb200_map_subspot2ref", "bsb200_compute_corr", "bsb200_init_cluster",
+    "bsb200_set_snapshot_sink", "bsb200_chain_file_open", "bsb200_chain_file_close", "bsb200_map_subspot2ref", "bsb200_compute_corr", "bsb200_init_cluster",
 ]
 
 _lib = None

@@ -754,11 +754,18 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
   // A snapshot staged in pinned memory is copied into the caller's matrices while the GPU already runs the next batch
   // (the copy touches fresh pages of a 1.3 GB allocation at 10M spots: ~30 ms per row that used to idle the GPU).
   int64_t pending_row = -1;
+  int sink_rc = BSB200_OK;
   auto flush_pending = [&]() {
     if (pending_row < 0) return;
     const size_t r = (size_t) pending_row;
     if (out->z) std::memcpy(out->z + r * ch->n + ch->lo, ch->h_snap_z, sizeof(int32_t) * ch->n_own);
     if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n + ch->lo, ch->h_snap_w, sizeof(double) * ch->n_own);
+    if (sink_active() && ch->world() == 1) {   // chain persistence: the row goes to the sink as it is produced
+      const int64_t dims[1] = {ch->n};
+      int rc = sink_write("z", (int64_t) r, ch->h_snap_z, ch->n, 0, dims, 1);
+      if (!rc && ch->tdist) rc = sink_write("weights", (int64_t) r, ch->h_snap_w, ch->n, 1, dims, 1);
+      if (rc && !sink_rc) sink_rc = rc;
+    }
     out->rows_done = (int32_t) r + 1;
     pending_row = -1;
   };
@@ -780,7 +787,8 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
     const bool boundary = (ch->iters_done + 1) % ch->thin == 0;
     if (boundary) {
       const int64_t row = (ch->iters_done + 1) / ch->thin;
-      const bool want_w = ch->tdist && (!out || out->weights);
+      const bool sink = sink_active() && out && ch->world() == 1;
+      const bool want_w = ch->tdist && (!out || out->weights || sink);
       launch_snapshot(ch->z.p, want_w ? ch->w.p : nullptr, ch->orig.p, ch->n_pos, ch->snap_z.p,
                       want_w ? ch->snap_w.p : nullptr, s, ch->lo);
       if (out && out->z_mode && row >= out->mode_from && row < ch->nrep / ch->thin + 1) {
@@ -793,7 +801,7 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
         launch_mode_accumulate(ch->snap_z.p, ch->n_own, ch->q, (uint32_t) row, ch->mode_cnt.p, ch->mode_first.p, s);
       }
       // the snapshots travel to the host only when the caller asked for the matrices
-      if (!out || out->z) CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
+      if (!out || out->z || sink) CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
       if (want_w) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(ch->ev1, s));
@@ -817,6 +825,7 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
   }
   flush_pending();
   if (device_ms) *device_ms = total_ms;
+  if (sink_rc) return sink_rc;
   return check_device_error(ch);
 }
 
@@ -1008,6 +1017,14 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
     if (out->z) std::memset(out->z + n, 0, sizeof(int32_t) * n);
     if (out->weights && ch->tdist) std::memset(out->weights + n, 0, sizeof(double) * n);
   }
+  if (sink_active() && !sharded) {   // row 0 = initial state
+    const int64_t dims[1] = {n};
+    if ((rc = sink_write("z", 0, args->init, n, 0, dims, 1))) return rc;
+    if (ch->tdist) {
+      std::vector<double> ones((size_t) n, 1.0);
+      if ((rc = sink_write("weights", 0, ones.data(), n, 1, dims, 1))) return rc;
+    }
+  }
   out->rows_done = 1;
   out->ncolours = ch->ord.ncol;
   out->setup_ms = ch->setup_ms;
@@ -1030,6 +1047,16 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   if (out->lambda)
     for (int k = 0; k < nl; k++) std::memcpy(out->lambda + (size_t) k * d * d, args->lambda0, sizeof(double) * d * d);
   if (rc == BSB200_OK) out->rows_done = nsnap;
+  if (sink_active() && !sharded && out->mu && out->lambda && out->plogLik) {   // the small parameters, all rows at once
+    const int64_t dmu[2] = {q, d}, dlam[3] = {nl, d, d}, one[1] = {1};
+    int rc3 = BSB200_OK;
+    for (int r = 0; r < out->rows_done && !rc3; r++) {
+      rc3 = sink_write("mu", r, out->mu + (size_t) r * q * d, (int64_t) q * d, 1, dmu, 2);
+      if (!rc3) rc3 = sink_write("lambda", r, out->lambda + (size_t) r * nl * d * d, (int64_t) nl * d * d, 1, nl > 1 ? dlam : dlam + 1, nl > 1 ? 3 : 2);
+    }
+    for (int i = 0; i < args->nrep && !rc3; i++) rc3 = sink_write("plogLik", i, out->plogLik + i, 1, 1, one, 1);
+    if (rc3) return rc3;
+  }
   return rc;
 }
 

@@ -19,6 +19,9 @@ extern bsb200_poll_fn g_poll;
 extern void *g_poll_user;
 // bsb200_cancel() seen, or the registered interrupt poll asks to stop (include/bsb200.h)
 bool cancel_requested();
+// snapshot sink (chain_file.cpp): rows of z / weights / Y as they are produced, mu / lambda / plogLik / Ychange at the end
+bool sink_active();
+int sink_write(const char *param, int64_t row, const void *data, int64_t count, int is_f64, const int64_t *dims, int ndims);
 
 // Records the message bsb200_last_error() returns and hands back `code`.
 int fail(int code, const char *fmt, ...);

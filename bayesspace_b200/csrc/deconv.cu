@@ -264,6 +264,32 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
     }
     g_launches.store(launches_before);
   }
+  // ---- chain persistence: rows go to the registered sink as they are produced (staged here when the caller did not
+  //      ask for the matrices themselves)
+  const bool sink = sink_active();
+  std::vector<int32_t> sink_z;
+  std::vector<double> sink_w, sink_Y, sink_Yt;
+  if (sink) {
+    if (!out->z) sink_z.resize((size_t) n);
+    if (!out->weights) sink_w.resize((size_t) n);
+    if (!out->Y) sink_Y.resize((size_t) n * d);
+    sink_Yt.resize((size_t) n * d);
+  }
+  auto sink_row = [&](size_t r, const int32_t *zr, const double *wr, const double *Yr) -> int {
+    const int64_t dn[1] = {n}, dY[2] = {n, d};
+    int rc2 = sink_write("z", (int64_t) r, zr, n, 0, dn, 1);
+    if (!rc2) rc2 = sink_write("weights", (int64_t) r, wr, n, 1, dn, 1);
+    if (!rc2) {   // as.vector(t(Y_r)): spot-major rows of d values (R/mcmcChain.R:206-211)
+      for (int64_t j = 0; j < n; j++)
+        for (int c = 0; c < d; c++) sink_Yt[(size_t) j * d + c] = Yr[(size_t) c * n + j];
+      rc2 = sink_write("Y", (int64_t) r, sink_Yt.data(), n * d, 1, dY, 2);
+    }
+    return rc2;
+  };
+  if (sink) {
+    std::vector<double> ones((size_t) n, 1.0);
+    if ((rc = sink_row(0, a->init, ones.data(), a->Y))) return rc;
+  }
   // ---- row 0 of the outputs (:793-801) -------------------------------------------------------------
   if (out->z) {
     std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
@@ -300,7 +326,7 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
       for (int rr = 0; rr < S; rr++) {
         launch_snapshot(z.p + (size_t) rr * ld0, w.p + (size_t) rr * ld0, orig0.p, n0, snap_z.p + (size_t) rr * n0,
                         snap_w.p + (size_t) rr * n0, s);
-        if (out->Y || out->Y_mean)
+        if (out->Y || out->Y_mean || sink)
           launch_snapshot_Y(Y.p + (size_t) rr * ld0, (int64_t) S * ld0, n0, d, orig0.p, ybar.p, snap_Y.p + (size_t) rr * n0, n, s);
       }
       if (out->Y_mean && (int) r >= out->mean_from) {
@@ -310,8 +336,11 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
       if (out->z_mode && (int) r >= out->mode_from && r < (size_t) nsnap)
         launch_mode_accumulate(snap_z.p, n, q, (uint32_t) r, mode_cnt.p, mode_first.p, s);
       if (out->z) CK(cudaMemcpyAsync(out->z + r * n, snap_z.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+      else if (sink) CK(cudaMemcpyAsync(sink_z.data(), snap_z.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
       if (out->weights) CK(cudaMemcpyAsync(out->weights + r * n, snap_w.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      else if (sink) CK(cudaMemcpyAsync(sink_w.data(), snap_w.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
       if (out->Y) CK(cudaMemcpyAsync(out->Y + r * (size_t) n * d, snap_Y.p, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+      else if (sink) CK(cudaMemcpyAsync(sink_Y.data(), snap_Y.p, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaEventRecord(run.ev1, s));
     CK(cudaStreamSynchronize(s));
@@ -319,6 +348,11 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
     CK(cudaEventElapsedTime(&ms, run.ev0, run.ev1));
     total_ms += ms;
     if (boundary) {
+      if (sink && r < (size_t) nsnap) {
+        const int rc2 = sink_row(r, out->z ? out->z + r * n : sink_z.data(), out->weights ? out->weights + r * n : sink_w.data(),
+                                 out->Y ? out->Y + r * (size_t) n * d : sink_Y.data());
+        if (rc2) return rc2;
+      }
       out->rows_done = (int32_t) r + 1;
       int e = 0;
       CK(cudaMemcpy(&e, err.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -348,6 +382,19 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
     for (int k = 0; k < q; k++)
       for (int c = 0; c < d; c++) out->mu[k * d + c] = a->mu0[c];
   if (out->lambda) std::memcpy(out->lambda, a->lambda0, sizeof(double) * d * d);
+  if (sink && out->mu && out->lambda && out->plogLik && out->Ychange) {   // the small parameters, all rows at once
+    const int64_t dmu[2] = {q, d}, dlam[2] = {d, d}, one[1] = {1};
+    int rc3 = BSB200_OK;
+    for (int r = 0; r < out->rows_done && !rc3; r++) {
+      rc3 = sink_write("mu", r, out->mu + (size_t) r * q * d, (int64_t) q * d, 1, dmu, 2);
+      if (!rc3) rc3 = sink_write("lambda", r, out->lambda + (size_t) r * d * d, (int64_t) d * d, 1, dlam, 2);
+    }
+    for (int i = 0; i < a->nrep && !rc3; i++) {
+      rc3 = sink_write("plogLik", i, out->plogLik + i, 1, 1, one, 1);
+      if (!rc3) rc3 = sink_write("Ychange", i, out->Ychange + i, 1, 1, one, 1);
+    }
+    if (rc3) return rc3;
+  }
   return status;
 }
 

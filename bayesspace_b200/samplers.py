@@ -196,7 +196,7 @@ def cluster(Y, q, df_j, init=None, model="t", precision="equal", mu0=None, lambd
 
 def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin, n, n0, d, gamma, q, init,
                    subspots, verbose, jitter_scale, adapt_before, c, mu0, lambda0, alpha, beta, thread_num=1,
-                   seed=0, device=0, keep_Y=True, mean_from=None, mode_from=None):
+                   seed=0, device=0, keep_Y=True, mean_from=None, mode_from=None, keep_z=True, keep_weights=True):
     """iterate_deconv (src/cluster.cpp:742-1141).  spot_neighbors: "a,b,c" strings / None (NA), or a
     CSR tuple.  Y (n x d) is not mutated (quirk Q10).  mean_from: also return the running mean of the
     Y snapshots r >= mean_from as 'Y_mean' (what spatialEnhance computes, R/spatialEnhance.R:441); mode_from: also
@@ -221,10 +221,10 @@ def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin
     if Y.shape != (n, d) or pos.shape != (n, 2) or len(np.asarray(init)) != n or len(sp) != n0 + 1:
         raise _lib.BayesSpaceError(_lib.ERR_INVALID, "Invalid arguments!")
     nsnap = nrep // thin + 1
-    z = np.zeros((nsnap, n), dtype=np.int32)
+    z = np.zeros((nsnap, n), dtype=np.int32) if keep_z else None
     mu = np.zeros((nsnap, q * d))
     lam = np.zeros((nsnap, d * d))
-    w = np.zeros((nsnap, n))
+    w = np.zeros((nsnap, n)) if keep_weights else None
     Yo = np.zeros((nsnap, d, n)) if keep_Y else None
     Ym = np.zeros((d, n)) if mean_from is not None else None
     ych, pl = np.zeros(nrep), np.zeros(nrep)
@@ -236,9 +236,13 @@ def iterate_deconv(subspot_positions, dist, spot_neighbors, Y, tdist, nrep, thin
     o.z_mode, o.mode_from = ptr(zm), 0 if mode_from is None else int(mode_from)
     o.Ychange, o.plogLik, o.df_j = ptr(ych), ptr(pl), ptr(dfj)
     check(lib().bsb200_deconv(C.byref(a), C.byref(o)))
-    out = {"z": z, "mu": mu, "lambda": lam.reshape(nsnap, d, d).transpose(0, 2, 1), "weights": w, "Ychange": ych,
+    out = {"mu": mu, "lambda": lam.reshape(nsnap, d, d).transpose(0, 2, 1), "Ychange": ych,
            "plogLik": pl, "df_j": dfj.reshape(4, n).T.copy(),
            "_info": {"ncolours": o.ncolours, "setup_ms": o.setup_ms, "device_ms": o.device_ms, "rows_done": o.rows_done}}
+    if keep_z:
+        out["z"] = z
+    if keep_weights:
+        out["weights"] = w
     if keep_Y:
         out["Y"] = Yo.transpose(0, 2, 1)   # nsnap x n x d
     if mean_from is not None:

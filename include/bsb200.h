@@ -65,6 +65,25 @@ typedef int (*bsb200_poll_fn)(void *user);
 void bsb200_set_interrupt_poll(bsb200_poll_fn poll, void *user);
 int bsb200_device_count(void);
 
+/* Chain persistence (R/mcmcChain.R:48-73, :181-223): instead of materialising the snapshot matrices, a sampler call
+ * hands every snapshot row to a registered sink as it is produced -- "z" (int32, n), "weights" (f64, n) and, for
+ * bsb200_deconv, "Y" (f64, n x d flattened ROW-major like as.vector(t(Y))) at every thin boundary (row 0 = initial
+ * state), then once at the end "mu" (row r: q x d), "lambda" (row r: nl x d x d), "plogLik" and "Ychange" (row i: 1).
+ * `dims` is the per-row shape mcmcChain.R stores as the dataset's "dims" attribute.  With a sink registered z /
+ * weights / Y may be NULL in the *_out structs (BASELINE config C3: 7.2 GB of Y snapshots never sit in host memory).
+ * A non-zero return of write() fails the call with BSB200_ERR_BUFFER.  One sink per process; NULL unregisters. */
+typedef struct bsb200_sink {
+  int (*write)(void *user, const char *param, int64_t row, const void *data, int64_t count, int32_t is_f64,
+               const int64_t *dims, int32_t ndims);
+  void *user;
+} bsb200_sink;
+void bsb200_set_snapshot_sink(const bsb200_sink *sink);
+/* Built-in sink: a directory with one raw little-endian file per parameter ("<param>.bin", one row per kept
+ * iteration) and "meta.json" (dtype, rows, cols, dims) -- the layout of mcmcChain.R's HDF5 datasets without libhdf5
+ * (reader: INTEGRATION.md).  open registers the sink, close writes meta.json and unregisters it. */
+int bsb200_chain_file_open(const char *dir);
+int bsb200_chain_file_close(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Neighbour construction (host).  Two-pass sizing: call with idx == NULL (or too small a capacity)
  * to obtain *nnz, then again with a buffer of that many entries.
