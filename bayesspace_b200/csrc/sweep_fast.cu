@@ -21,6 +21,7 @@
 //    second Marsaglia-Tsang test decided by a single-precision screen with an exact FP64 fallback (rng.cuh);
 //  * parameters are read from shared memory as 16-byte broadcasts; the Potts scale 2 gamma / |N_j| is a table;
 //    the neighbour loop is unrolled for the lattice degrees (4 and 6).
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.hpp"
@@ -486,6 +487,22 @@ int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   static size_t granted[64] = {};
   const cudaError_t e = ensure_dynamic_smem(k_sweep_fast<D, TDIST, NH>, L.bytes, granted);
   if (e != cudaSuccess) return (int) e;
+  // Persistent launch: at most as many CTAs as the device holds at once, each walking its segments (seg = blockIdx.x,
+  // + gridDim.x, ...).  The per-CTA set-up (parameter staging, logarithm table, barrier initialisation) is then paid
+  // once per CTA instead of once per segment; the segments, their records and the fold order do not change.
+  static int slots[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int resident = dev >= 0 && dev < 64 ? slots[dev] : 0;
+  if (!resident) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH>, kBlock, L.bytes);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = per_sm > 0 && sms > 0 ? per_sm * sms : grid;
+    if (dev >= 0 && dev < 64) slots[dev] = resident;   // for the largest q seen first; smaller q only fit better
+  }
+  static const bool persistent = std::getenv("BSB200_NO_PERSISTENT_SWEEP") == nullptr;
+  if (persistent && grid > resident) grid = resident;
   k_sweep_fast<D, TDIST, NH><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
   return 0;
 }
