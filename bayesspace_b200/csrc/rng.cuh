@@ -150,9 +150,9 @@ __device__ __forceinline__ int propose_label_bits(int z_prev, int q, uint32_t bi
 __device__ __forceinline__ bool mh_accept(double delta, double u) {
   const double v = (delta >= -0.69314718055994530942) ? u : 1.0 - u;
   const float lf = __logf((float) v);
-  const double gap = delta - (double) lf;
-  const bool decisive = fabs(gap) > 1e-4 * (1.0 + fabs((double) lf));
-  bool acc = (delta >= 0.0) | (decisive & (gap > 0.0));
+  const float gap = (float) (delta - (double) lf);   // the margin test itself runs in single precision (FMA pipe)
+  const bool decisive = fabsf(gap) > 1e-4f * (1.0f + fabsf(lf));
+  bool acc = (delta >= 0.0) | (decisive & (gap > 0.0f));
   if (!decisive && delta < 0.0) acc = sample_two(exp(delta), u);
   return acc;
 }
@@ -203,9 +203,9 @@ __device__ __forceinline__ bool mt_attempt(double x, double u, double dd, double
   const double x2 = x * x;
   const bool squeeze = u < 1.0 - 0.0331 * x2 * x2;
   const float lu = __logf((float) u), lv = __logf((float) v3);
-  const double gap = (0.5 * x2 + dd * ((1.0 - v3) + (double) lv)) - (double) lu;
-  const bool decisive = fabs(gap) > 1e-4 * (1.0 + fabs((double) lu) + dd * (1.0 + fabs((double) lv)));
-  bool ok = (v > 0.0) & (squeeze | (decisive & (gap > 0.0)));
+  const float gap = (float) ((0.5 * x2 + dd * ((1.0 - v3) + (double) lv)) - (double) lu);
+  const bool decisive = fabsf(gap) > 1e-4f * (1.0f + fabsf(lu) + (float) dd * (1.0f + fabsf(lv)));
+  bool ok = (v > 0.0) & (squeeze | (decisive & (gap > 0.0f)));
   if (v > 0.0 && !squeeze && !decisive) ok = log(u) < 0.5 * x2 + dd * (1.0 - v3 + log(v3));
   return ok;
 }

@@ -151,14 +151,15 @@ __device__ __forceinline__ void dot3(const double (&y)[D], const double *__restr
 
 constexpr int kNbInline = 6;   // neighbour slots handled in the straight-line part (hex lattice degree); the rest in a loop
 
-template <int D, bool TDIST, int NH>
+template <int D, bool TDIST, int NH, bool LEAN>
 __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     k_sweep_fast(const __grid_constant__ SweepArgs a, const __grid_constant__ SweepMaps maps) {
   extern __shared__ __align__(1024) unsigned char smdyn[];
   constexpr int NP = D * (D + 1) / 2, RS = D + (D & 1) + 2;   // RS = 2 (mod 16) doubles: rows of different clusters start in different banks
   constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, DP = TileGeom<D>::DP;
   constexpr int YBOX = DP * kRowB;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: TMA operands stay in uniform registers
   const int q = a.PL.q, E = a.SL.E;
   const FastSmem L = fast_smem_layout(D, q, E, TDIST, NH, a.maxdeg);
   unsigned char *smraw = smdyn + ((1024u - (smem_u32(smdyn) & 1023u)) & 1023u);   // 1024-byte aligned base
@@ -177,7 +178,9 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   double *cfold = reinterpret_cast<double *>(smraw + L.shared_bytes);   // + warp * warp_stride / 8
   const int fold_stride = L.warp_stride / 8;
 
-  const bool stats_only = a.flags & SW_STATS_ONLY, dry = a.flags & SW_DRY;
+  // LEAN: the instantiation of the sampling loop proper (no probe flags): the statistics-only and dry-run paths are
+  // compiled out, which keeps the hot loop's code -- and its instruction-cache footprint -- small
+  const bool stats_only = !LEAN && (a.flags & SW_STATS_ONLY), dry = !LEAN && (a.flags & SW_DRY);
   if (*a.err) return;
   if (!stats_only) {
     const double *Pm = a.params;
@@ -480,12 +483,12 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   }
 }
 
-template <bool TDIST, int NH>
+template <bool TDIST, int NH, bool LEAN>
 int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
   const FastSmem L = fast_smem_layout(D, a.PL.q, a.SL.E, TDIST, NH, a.maxdeg);
   static size_t granted[64] = {};
-  const cudaError_t e = ensure_dynamic_smem(k_sweep_fast<D, TDIST, NH>, L.bytes, granted);
+  const cudaError_t e = ensure_dynamic_smem(k_sweep_fast<D, TDIST, NH, LEAN>, L.bytes, granted);
   if (e != cudaSuccess) return (int) e;
   // Persistent launch: at most as many CTAs as the device holds at once, each walking its segments (seg = blockIdx.x,
   // + gridDim.x, ...).  The per-CTA set-up (parameter staging, logarithm table, barrier initialisation) is then paid
@@ -496,22 +499,28 @@ int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   int resident = dev >= 0 && dev < 64 ? slots[dev] : 0;
   if (!resident) {
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH>, kBlock, L.bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH, LEAN>, kBlock, L.bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     resident = per_sm > 0 && sms > 0 ? per_sm * sms : grid;
     if (dev >= 0 && dev < 64) slots[dev] = resident;   // for the largest q seen first; smaller q only fit better
   }
   static const bool persistent = std::getenv("BSB200_NO_PERSISTENT_SWEEP") == nullptr;
   if (persistent && grid > resident) grid = resident;
-  k_sweep_fast<D, TDIST, NH><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
+  k_sweep_fast<D, TDIST, NH, LEAN><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
   return 0;
 }
 
 // shared precision, q <= kFastMaxQ only (the caller checks)
 void launch_fast(int tdist, const SweepArgs &a, int grid, cudaStream_t s) {
   const int nh = (a.PL.q + 7) / 8;
-  if (tdist) { if (nh == 1) launch_fast_t<true, 1>(a, grid, s); else launch_fast_t<true, 2>(a, grid, s); }
-  else { if (nh == 1) launch_fast_t<false, 1>(a, grid, s); else launch_fast_t<false, 2>(a, grid, s); }
+  const bool lean = !(a.flags & (SW_STATS_ONLY | SW_DRY));
+  if (lean) {
+    if (tdist) { if (nh == 1) launch_fast_t<true, 1, true>(a, grid, s); else launch_fast_t<true, 2, true>(a, grid, s); }
+    else { if (nh == 1) launch_fast_t<false, 1, true>(a, grid, s); else launch_fast_t<false, 2, true>(a, grid, s); }
+  } else {
+    if (tdist) { if (nh == 1) launch_fast_t<true, 1, false>(a, grid, s); else launch_fast_t<true, 2, false>(a, grid, s); }
+    else { if (nh == 1) launch_fast_t<false, 1, false>(a, grid, s); else launch_fast_t<false, 2, false>(a, grid, s); }
+  }
 }
 
 size_t fast_smem(int tdist, const SweepArgs &a) {
