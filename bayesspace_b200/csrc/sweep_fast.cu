@@ -69,7 +69,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(int D, int q, int E, bool t
   s.orig = w; w += 2 * kRowB;
   s.wst = w; w += 32 * 8;
   s.zst = w; w += 32;
-  s.skacc = w; w += q * DP * 8;   // per-cluster sums of the label-uniform sub-tiles (rows 0..d-1: s_k, row d: n_k)
+  s.skacc = w; w += (D <= 16 ? q * DP * 8 : 0);   // per-cluster sums of the label-uniform sub-tiles (rows 0..d-1: s_k, row d: n_k)
   s.warp_stride = (w + 1023) & ~1023;
   s.bytes = (size_t) s.shared_bytes + (size_t) kWarps * s.warp_stride + 1024;   // + slack to align the base
   return s;
@@ -92,6 +92,9 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 
 constexpr int fast_min_blocks(int D) { return D <= 16 ? 4 : (D <= 24 ? 3 : 2); }
+// The cluster sums of label-uniform sub-tiles come from the second moments' constant-row column (below) when the
+// per-warp accumulators fit next to four resident CTAs; larger d keep the shared memory for occupancy instead.
+__host__ __device__ constexpr bool fast_uniform_shortcut(int D) { return D <= 16; }
 
 // x^T P x with P = packed upper triangle, COLUMN by column (b outer, a <= b inner, off-diagonals doubled), read as
 // 16-byte broadcasts.  Consecutive FMAs of a column go to different accumulators s[a], so the FP64 latency of one
@@ -239,7 +242,8 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     const int nsub = (count + 31) >> 5;
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
-    for (int e = lane; e < q * DP; e += 32) skacc[e] = 0.0;
+    if (fast_uniform_shortcut(D))
+      for (int e = lane; e < q * DP; e += 32) skacc[e] = 0.0;
     double hp_acc = 0.0, nacc = 0.0, lw_m = 1.0;
     int lw_e = 0;
     double C[NTILES][2], CH[NT][NH][2];
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         wst[lane] = wj;
         zst[lane] = (uint8_t) zfinal;
         const int zf0 = __shfl_sync(0xffffffffu, zfinal, 0);
-        const bool uniform = do_pairs && __all_sync(0xffffffffu, !active || zfinal == zf0);
+        const bool uniform = fast_uniform_shortcut(D) && do_pairs && __all_sync(0xffffffffu, !active || zfinal == zf0);
         __syncwarp();
         // tile (i, NT-1) has index i*NT - i(i-1)/2 + NT-1-i in the upper-triangular enumeration
         double snap[NT];
@@ -470,7 +474,9 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
 #pragma unroll
       for (int w = 0; w < kWarps; w++)
         s += cfold[(size_t) w * fold_stride + t * 64 + (r & 7) * 8 + (k & 7)] +
-             reinterpret_cast<const double *>(smraw + L.shared_bytes + (size_t) w * L.warp_stride + L.skacc)[k * DP + r];
+             (fast_uniform_shortcut(D)
+                  ? reinterpret_cast<const double *>(smraw + L.shared_bytes + (size_t) w * L.warp_stride + L.skacc)[k * DP + r]
+                  : 0.0);
       if (r < D) acc[a.SL.sk + k * D + r] = s;
       else acc[a.SL.nk + k] = s;
     }
