@@ -210,17 +210,17 @@ int choose_segment(int64_t n, int ncol, int d) {
   tps = std::max<int64_t>(1, std::min<int64_t>(8, tps));
   if (choose_groups(n) == kGroups && ncol > 0) {
     // Sharded sizes: a colour phase of W ranks has (kGroups / W) * ceil(tiles / t) segments for 148 SMs x (resident
-    // CTAs of k_sweep_fast<d>) persistent CTAs; its time is about rounds * (t + fixed cost of a segment, ~0.15 tile:
-    // record fold and write).  Pick the t whose cost, summed over W = 1, 2, 4, 8, is smallest (10M spots, d = 15:
-    // t = 9 -> 8 / 4 / 2 / 1 rounds; 700k bins, d = 20: t = 1 -> 7 / 4 / 2 / 1).
+    // CTAs of k_sweep_fast<d>) persistent CTAs; its time is about rounds * (t + fixed cost of a segment, ~half a tile:
+    // record fold and write -- one-tile segments measured slower than two-tile ones at 700k bins).  Pick the t whose
+    // cost, summed over W = 1, 2, 4, 8, is smallest (10M spots, d = 15: t = 9 -> 8 / 4 / 2 / 1 rounds).
     const int64_t slots = 148 * (d <= 16 ? 4 : (d <= 24 ? 3 : 2));
     const int64_t tiles = ((n / kGroups + ncol - 1) / ncol + kBlock - 1) / kBlock;   // per (shard, colour)
     int64_t best = 0;
     double best_cost = 0;
-    for (int64_t t = 1; t <= 12; t++) {
+    for (int64_t t = 2; t <= 12; t++) {
       const int64_t segs = (tiles + t - 1) / t;
       double cost = 0;
-      for (int W = 1; W <= 8; W *= 2) cost += (double) ((kGroups / W * segs + slots - 1) / slots) * ((double) t + 0.15) * W;
+      for (int W = 1; W <= 8; W *= 2) cost += (double) ((kGroups / W * segs + slots - 1) / slots) * ((double) t + 0.5) * W;
       if (best == 0 || cost < best_cost) { best = t; best_cost = cost; }
     }
     tps = best;
