@@ -274,6 +274,9 @@ struct bsb200_chain {
   int comm_rc = 0;               // first NCCL failure seen while enqueuing (reported by the next sync point)
   double *gsum_p = nullptr;      // shard sums: own buffer, or the exported window of the peer transport
   SweepMaps maps;                // TMA descriptors of Y / ell / orig
+  bool fused_halo = false;       // peer transport + k_sweep_fast: the sweep launches exchange the halos themselves
+  std::vector<int> nbound;       // per colour: boundary segments (first in the launch list)
+  DevBuf<uint32_t> halo_done;    // per colour: finished boundary segments of the running launch
   bool have_maps = false;
 
   ~bsb200_chain() {
@@ -302,6 +305,15 @@ struct bsb200_chain {
     a.iter = iter.p; a.iter_add = iter_add;
     a.key0 = (uint32_t) seed; a.key1 = (uint32_t) (seed >> 32);
     a.gamma = gamma; a.flags = flags | sweep_flags; a.err = err.p;
+    if (fused_halo && colour >= 0 && !(flags & SW_STATS_ONLY)) {
+      a.halo.legs = comm.halo_legs + (size_t) colour * (size_t) (world() - 1);
+      a.halo.nlegs = comm.halo_leg_count[(size_t) colour];
+      a.halo.nbound = nbound[(size_t) colour];
+      a.halo.ncol = ord.ncol; a.halo.colour = colour;
+      a.halo.send_pos = send_pos.p; a.halo.send_dst = comm.send_dst;
+      a.halo.done = halo_done.p + colour;
+      a.halo.timeout_ns = (unsigned long long) comm.peer_timeout_ns;
+    }
     return a;
   }
   ParamArgs param_args(bool finalize_only) const {
@@ -342,6 +354,10 @@ struct bsb200_chain {
   // labels of the boundary spots of one colour travel to the ranks that hold them as ghosts
   void enqueue_halo(int colour, cudaStream_t s) {
     if (world() <= 1) return;
+    if (fused_halo) {   // the sweep launch of this colour pushed and released already; an empty phase still owes its epoch
+      if (ord.colour_seg_start[(size_t) colour + 1] == ord.colour_seg_start[(size_t) colour]) comm.enqueue_halo_release(colour, iter.p, s);
+      return;
+    }
     if (comm.peer()) {
       comm.enqueue_halo_peer(colour, z.p, send_pos.p, err.p, s);
       return;
@@ -535,6 +551,42 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     rc = ch->comm.init(world, rank, a->comm_id);
     if (rc) return rc;
     mark("comm init");
+    // Fused halo exchange (layout.hpp HaloFuse): segments that hold boundary spots move to the front of their
+    // colour's launch list.  The list order does not enter the arithmetic (records are addressed by slot).
+    static const bool no_fuse = std::getenv("BSB200_NO_FUSED_HALO") != nullptr;
+    ch->fused_halo = ch->comm.peer() && !no_fuse && K.sweep_fast && !ch->vvv && q <= kFastMaxQ &&
+                     !std::getenv("BSB200_NO_FAST_SWEEP");
+    if (ch->fused_halo) {
+      SpotOrder &o = ch->ord;
+      ch->nbound.assign((size_t) ncol, 0);
+      for (int c = 0; c < ncol; c++) {
+        const int s0 = o.colour_seg_start[(size_t) c], s1 = o.colour_seg_start[(size_t) c + 1];
+        if (s1 == s0) continue;
+        std::vector<char> isb((size_t) (s1 - s0), 0);
+        for (int p = 0; p < world; p++) {
+          const size_t e = (size_t) c * world + p;
+          for (int32_t k = ch->halo.send_off[e]; k < ch->halo.send_off[e + 1]; k++) {
+            const int32_t pos = ch->halo.send_pos[(size_t) k];
+            // segments of a colour are sorted by their first position
+            const auto it2 = std::upper_bound(o.seg_begin.begin() + s0, o.seg_begin.begin() + s1, pos);
+            const int sidx = (int) (it2 - (o.seg_begin.begin() + s0)) - 1;
+            if (sidx >= 0) isb[(size_t) sidx] = 1;
+          }
+        }
+        std::vector<int32_t> nb2, nc2, ns2;
+        int nbnd = 0;
+        for (int pass = 0; pass < 2; pass++)
+          for (int i = 0; i < s1 - s0; i++)
+            if ((isb[(size_t) i] != 0) == (pass == 0)) {
+              nb2.push_back(o.seg_begin[(size_t) (s0 + i)]); nc2.push_back(o.seg_count[(size_t) (s0 + i)]); ns2.push_back(o.seg_slot[(size_t) (s0 + i)]);
+              if (pass == 0) nbnd++;
+            }
+        std::copy(nb2.begin(), nb2.end(), o.seg_begin.begin() + s0);
+        std::copy(nc2.begin(), nc2.end(), o.seg_count.begin() + s0);
+        std::copy(ns2.begin(), ns2.end(), o.seg_slot.begin() + s0);
+        ch->nbound[(size_t) c] = std::max(nbnd, 1);   // no boundary spot of this colour: the first segment keeps the handshake
+      }
+    }
   }
 
   // ---- device staging --------------------------------------------------------------------------
@@ -688,6 +740,8 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if ((rc = ch->snap_z.alloc((size_t) n_own))) return rc;
   if ((rc = ch->snap_w.alloc((size_t) n_own))) return rc;
   if ((rc = ch->iter.alloc(1))) return rc;
+  if ((rc = ch->halo_done.alloc((size_t) std::max(ncol, 1)))) return rc;
+  CK(cudaMemsetAsync(ch->halo_done.p, 0, sizeof(uint32_t) * std::max(ncol, 1), s));
   if ((rc = ch->err.alloc(1))) return rc;
   CK(cudaMemsetAsync(ch->iter.p, 0, sizeof(uint32_t), s));
   CK(cudaMemsetAsync(ch->err.p, 0, sizeof(int), s));

@@ -1,6 +1,7 @@
 // comm.cpp -- the transports of the spot-sharded chain (see comm.hpp): peer-memory stores with epoch flags
 // (CUDA IPC, host rendezvous in POSIX shared memory) and the run-time-bound NCCL baseline.
 #include "comm.hpp"
+#include "peer_sync.cuh"
 
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -194,33 +195,6 @@ class ShmRendezvous {
 // ---- device side of the peer transport ----------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait for a peer's epoch.  Once any error is latched nobody waits any more (flags are still sent), so a
-// failed rank drains the captured graph instead of stalling its peers for one timeout per wait.
-__device__ void wait_flag(const uint32_t *flag, uint32_t epoch, int *err, unsigned long long timeout_ns) {
-  if (*(volatile int *) err) return;
-  const unsigned long long t0 = global_ns();
-  while ((int32_t) (ld_acquire_sys(flag) - epoch) < 0) {
-    __nanosleep(32);
-    if (global_ns() - t0 > timeout_ns) {
-      atomicCAS(err, 0, BSB_DEVERR_PEER_TIMEOUT);
-      return;
-    }
-  }
-}
-
 // One CTA per neighbouring rank: store the boundary labels of the colour just swept into the neighbour's ghost
 // slots, release the neighbour's flag, then wait until the neighbour's own labels of this colour have landed here.
 // WAR safety: the slots written belong to the colour just swept, which the neighbour reads only in LATER phases,
@@ -241,6 +215,12 @@ __global__ void __launch_bounds__(256) k_halo_peer(const HaloLeg *legs, const ui
     st_release_sys(L.peer_flag, e);
     wait_flag(L.my_flag, e, err, timeout_ns);
   }
+}
+
+// Fused-halo mode (k_sweep_fast pushes and waits itself, layout.hpp HaloFuse): epoch of an empty colour phase
+__global__ void k_halo_release(const HaloLeg *legs, int nlegs, const uint32_t *iter, int ncol, int colour) {
+  const int l = threadIdx.x;
+  if (l < nlegs) st_release_sys(legs[l].peer_flag, (*iter - 1u) * (uint32_t) ncol + (uint32_t) colour + 1u);
 }
 
 // One CTA per peer: store this rank's shard sums into the peer's window (parity of the new epoch), release, wait
@@ -491,6 +471,13 @@ void Comm::enqueue_halo_peer(int colour, const uint8_t *z, const int32_t *send_p
   if (nlegs == 0) return;
   k_halo_peer<<<nlegs, 256, 0, s>>>(halo_legs + (size_t) colour * (size_t) (world - 1), z, send_pos_dev, send_dst, counters,
                                     world, err, (unsigned long long) peer_timeout_ns);
+  g_launches++;
+}
+
+void Comm::enqueue_halo_release(int colour, const uint32_t *iter, cudaStream_t s) {
+  const int nlegs = halo_leg_count[(size_t) colour];
+  if (nlegs == 0) return;
+  k_halo_release<<<1, 32, 0, s>>>(halo_legs + (size_t) colour * (size_t) (world - 1), nlegs, iter, ncol, colour);
   g_launches++;
 }
 

@@ -92,6 +92,8 @@ struct Comm {
   // PEER data path
   void enqueue_halo_peer(int colour, const uint8_t *z, const int32_t *send_pos_dev, int *err, cudaStream_t s);
   void enqueue_gather_peer(size_t offset_doubles, size_t count_doubles, int *err, cudaStream_t s);
+  // fused-halo mode: a colour phase in which this rank sweeps nothing still owes its neighbours the phase's epoch
+  void enqueue_halo_release(int colour, const uint32_t *iter, cudaStream_t s);
 
   // NCCL data path.  in-place allgather: every rank contributes `count` doubles at buf + rank*count
   int allgather_f64(double *buf, size_t count, cudaStream_t s);

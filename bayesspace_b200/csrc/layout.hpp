@@ -90,6 +90,23 @@ enum SweepFlags : uint32_t {
 };
 
 struct SweepMaps;   // tma_maps.hpp
+struct HaloLeg;     // comm.hpp
+
+// Fused halo exchange of k_sweep_fast on the peer transport (one chain over several GPUs): the segments that hold
+// boundary spots come FIRST in a colour's launch list; each waits, before it starts, for the neighbours' labels of the
+// previous colour phase, and the CTA that finishes the last of them stores the boundary labels of this colour into the
+// neighbours' ghost slots and releases their flags -- while the interior segments are still being swept.
+// Epoch of (iteration it >= 1, colour c) = (it - 1) * ncol + c + 1; a phase waits for the epoch before it.
+struct HaloFuse {
+  const HaloLeg *legs;       // this colour's legs: every neighbouring rank, empty send lists included (device)
+  int nlegs;                 // 0: no fused exchange
+  int nbound;                // boundary segments = the first nbound entries of the launch list
+  int ncol, colour;
+  const int32_t *send_pos;   // own positions of the boundary labels, indexed by the legs' [s0, s1)
+  const int32_t *send_dst;   // their positions in the peer's label array
+  uint32_t *done;            // finished boundary segments of this launch (reset by the last one)
+  unsigned long long timeout_ns;
+};
 
 struct SweepArgs {
   const SweepMaps *maps;      // host pointer: TMA descriptors of Y / ell / orig (k_sweep_fast), may be null
@@ -114,6 +131,7 @@ struct SweepArgs {
   double gamma;
   uint32_t flags;
   int *err;
+  HaloFuse halo;              // fused halo exchange (k_sweep_fast, peer transport); nlegs == 0 otherwise
   int32_t *dry_znew;          // dry-run outputs, original spot order
   double *dry_w, *dry_hp, *dry_hn, *dry_prob;
   int32_t *dry_acc;

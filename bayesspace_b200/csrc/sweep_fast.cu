@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "kernels.hpp"
+#include "peer_sync.cuh"
 #include "pipeline.cuh"
 #include "rng.cuh"
 #include "tile_stats.cuh"
@@ -238,9 +239,20 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   const int kc = lane >> 2, lq = lane & 3;
   const int frag_row = kc * kRowB, frag_sw = ((lq >> 1) ^ kc) << 4, frag_lo = (lq & 1) << 3;
 
+  __shared__ int s_last_boundary;
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
     const int nsub = (count + 31) >> 5;
+    // fused halo exchange (HaloFuse, layout.hpp): a boundary segment first makes sure the neighbours' labels of the
+    // previous colour phase have landed in this rank's ghost slots
+    const bool bseg = a.halo.nlegs > 0 && seg < a.halo.nbound && !stats_only;
+    if (bseg) {
+      if (tid == 0) {
+        const uint32_t target = (it - 1u) * (uint32_t) a.halo.ncol + (dry ? 0u : (uint32_t) a.halo.colour);
+        for (int l = 0; l < a.halo.nlegs; l++) wait_flag(a.halo.legs[l].my_flag, target, a.err, a.halo.timeout_ns);
+      }
+      __syncthreads();
+    }
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     if (fast_uniform_shortcut(D))
       for (int e = lane; e < q * DP; e += 32) skacc[e] = 0.0;
@@ -483,6 +495,28 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
     for (int e = tid; e < E; e += kBlock) out[e] = acc[e];
+    if (bseg && !dry) {
+      // the CTA that completes the LAST boundary segment of this launch pushes the boundary labels of this colour to
+      // the neighbours and releases their flags; the interior segments of the launch are still running
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_last_boundary = atomicAdd(a.halo.done, 1u) == (uint32_t) (a.halo.nbound - 1);
+      __syncthreads();
+      if (s_last_boundary) {
+        __threadfence();
+        for (int l = 0; l < a.halo.nlegs; l++) {
+          const HaloLeg leg = a.halo.legs[l];
+          for (int k = leg.s0 + tid; k < leg.s1; k += kBlock) leg.peer_z[a.halo.send_dst[k]] = __ldcg(a.z + a.halo.send_pos[k]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+          const uint32_t epoch = (it - 1u) * (uint32_t) a.halo.ncol + (uint32_t) a.halo.colour + 1u;
+          for (int l = 0; l < a.halo.nlegs; l++) st_release_sys(a.halo.legs[l].peer_flag, epoch);
+          *a.halo.done = 0u;
+        }
+      }
+    }
     init_const_rows();     // the output tiles overwrote them
     fence_proxy_async();   // generic-proxy writes to the buffers before the next segment's TMA copies
     __syncthreads();
