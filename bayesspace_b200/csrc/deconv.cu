@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -194,6 +195,22 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
   if (out->Y_mean) CK(cudaMemsetAsync(Ymean.p, 0, sizeof(double) * n * d, s));
   if (out->z_mode) CK(cudaMemsetAsync(mode_cnt.p, 0, sizeof(uint32_t) * q * n, s));
 
+  // one launch for all colour classes needs every CTA resident at once (CTAs of a later class spin on the earlier ones)
+  DevBuf<int32_t> colour_seg_start;
+  DevBuf<uint32_t> colour_done;
+  if ((rc = upload(colour_seg_start, ord.colour_seg_start.data(), ord.colour_seg_start.size(), s)) ||
+      (rc = colour_done.alloc((size_t) std::max<int>(ncol, 1))))
+    return rc;
+  CK(cudaMemsetAsync(colour_done.p, 0, sizeof(uint32_t) * std::max<int>(ncol, 1), s));
+  bool fuse_colours = false;
+  {
+    int sms = 0, dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static const bool off = std::getenv("BSB200_NO_FUSED_DECONV") != nullptr;
+    // conservative: one CTA per SM is always resident whatever the kernel's registers / shared memory
+    fuse_colours = !off && ncol > 1 && (int) ord.seg_begin.size() <= 2 * sms;
+  }
   auto deconv_args = [&](int colour_id, int stats_only) {
     DeconvArgs k{};
     k.Y = Y.p; k.Y0 = Y0.p; k.z = z.p; k.w = w.p; k.ell = ell.p; k.maxdeg = maxdeg; k.orig0 = orig0.p;
@@ -205,6 +222,8 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
     k.key0 = (uint32_t) a->seed; k.key1 = (uint32_t) (a->seed >> 32);
     k.gamma = a->gamma; k.c = a->c; k.err_sd = err_sd; k.tdist = a->tdist ? 1 : 0; k.adaptive = adaptive ? 1 : 0;
     k.adapt_before = a->adapt_before; k.stats_only = stats_only; k.err = err.p;
+    k.fuse = (fuse_colours && colour_id < 0 && !stats_only) ? 1 : 0; k.ncol = ncol;
+    k.colour_seg_start = colour_seg_start.p; k.done = colour_done.p;
     return k;
   };
   auto param_args = [&](int finalize_only) {
@@ -225,6 +244,12 @@ static int deconv_impl(const bsb200_deconv_args *a, bsb200_deconv_out *out) {
   };
   auto enqueue_iteration = [&]() {
     enqueue_param(0);
+    if (fuse_colours) {   // every colour class in one launch, ordered by in-kernel counters (deconv.hpp)
+      DeconvArgs k = deconv_args(-1, 0);
+      K.deconv(k, k.nseg, s);
+      g_launches++;
+      return;
+    }
     for (int c = 0; c < ncol; c++) {
       DeconvArgs k = deconv_args(c, 0);
       if (k.nseg > 0) { K.deconv(k, k.nseg, s); g_launches++; }

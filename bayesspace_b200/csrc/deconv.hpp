@@ -38,6 +38,13 @@ struct DeconvArgs {
   double gamma, c, err_sd;
   int tdist, adaptive, adapt_before, stats_only;
   int *err;
+  // All colour classes in ONE launch (when every CTA of the launch is resident at once): only the label scan depends on
+  // the neighbouring parents' labels, so a CTA runs its Y / w updates at once and waits with its label scan until
+  // every CTA of the previous colour class has published its labels (done[c]: segments of colour c finished, counted
+  // over all iterations; target = iteration * segments of that colour).  fuse == 0: one launch per colour class.
+  int fuse, ncol;
+  const int32_t *colour_seg_start;   // ncol + 1 offsets into the launch list (colour-major)
+  uint32_t *done;                    // ncol counters
 };
 
 }   // namespace bsb

@@ -13,6 +13,7 @@
 // accumulates the sufficient statistics of the next iteration, so Y is read and written once.
 #include "deconv.hpp"
 #include "kernels.hpp"
+#include "peer_sync.cuh"
 #include "rng.cuh"
 #include "tile_stats.cuh"
 
@@ -82,6 +83,9 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const int begin = a.seg_begin[seg], count = a.seg_count[seg];
+    int my_colour = 0;
+    if (a.fuse)
+      while (my_colour + 1 < a.ncol && seg >= a.colour_seg_start[my_colour + 1]) my_colour++;
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
     for (int e = tid; e < (kBlock / 32) * stats_frags(D, nh) * 64; e += kBlock) ct[e] = 0.0;
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         j0 = (uint32_t) a.orig0[ip];
         sorig = (uint32_t) r * (uint32_t) a.n0 + j0;
       }
+      double dl_z = 0.0, u_acc_z = 0.0, hp_stay = 0.0, hp_move = 0.0;   // inputs of the label scan
+      int zn = 0, nacc_new = 0;
       if (!a.stats_only) {   // uniform branch
         double v[ADAPT ? D : 1];
 #pragma unroll
@@ -163,8 +169,6 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         double tot = 0.0;
         for (int rr = 0; rr < S; rr++) tot += __shfl_sync(0xffffffffu, dl, glane0 + rr);
         bool accY = false;
-        double dl_z = 0.0, u_acc_z = 0.0, hp_stay = 0.0, hp_move = 0.0;   // inputs of the label scan
-        int zn = 0, nacc_new = 0;
         if (active) {
           double probY = exp(tot);
           if (probY > 1.0) probY = 1.0;
@@ -229,10 +233,40 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           hp_stay = -0.5 * wj * lin_p;   // per-spot part of plogLik if the label stays
           hp_move = -0.5 * wj * lin_n;   // ... if it moves (:1035, :1048)
         }
+        if (ADAPT && active && r == 0) a.nacc[ip] = nacc_new;
+      }
+      // ---- stage sqrt(w) y; the second moments do not depend on the labels: they are folded BEFORE the label scan,
+      //      i.e. (one launch for all colour classes) while this CTA would otherwise wait for the previous class
+      {
+        const double sw = active ? sqrt(wj) : 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) tile[c * kTileLd + tid] = active ? sw * y[c] : 0.0;
+        sws[tid] = sw;
+        wvs[tid] = active ? wj : 0.0;
+        zs[tid] = 255;
+      }
+      __syncthreads();
+      tile_stats_mma<D>(ct, tile, zs, true, 0, warp, lane, nh);
+      if (!a.stats_only) {
         // ---- sequential label updates inside each parent: r = 0..S-1, neighbour labels live (:984,:1029-1051)
         // Neighbours in OTHER parents belong to another colour class and do not change during this launch: their
         // labels are gathered once, before the turns.  Neighbours inside the parent sit on adjacent lanes: their live
         // label is the lane's register, fetched by shuffle at every turn -- no memory traffic inside the scan.
+        if (a.fuse && my_colour > 0) {   // labels of the previous colour classes must be final and visible
+          if (tid == 0) {
+            const uint32_t target = it * (uint32_t) (a.colour_seg_start[my_colour] - a.colour_seg_start[my_colour - 1]);
+            const uint32_t *flag = a.done + (my_colour - 1);
+            const unsigned long long t0 = global_ns();
+            uint32_t v;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+              if ((int32_t) (v - target) >= 0 || *(volatile int *) a.err) break;
+              __nanosleep(64);
+              if (global_ns() - t0 > 20ull * 1000 * 1000 * 1000) { atomicCAS(a.err, 0, BSB_DEVERR_PEER_TIMEOUT); break; }
+            } while (true);
+          }
+          __syncthreads();
+        }
         constexpr int kNbReg = 8;
         int zu[kNbReg], src[kNbReg];
         int deg = 0;
@@ -246,7 +280,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
               deg++;
               const int32_t rr = nb / (int32_t) a.ld0, ipn = nb - rr * (int32_t) a.ld0;
               if (ipn == (int32_t) ip) src[ee] = glane0 + rr;   // same parent: live label of that lane
-              else zu[ee] = a.z[nb];
+              else zu[ee] = a.fuse ? (int) __ldcg(a.z + nb) : (int) a.z[nb];
             }
           }
         }
@@ -259,7 +293,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
               const int32_t rr = nb / (int32_t) a.ld0, ipn = nb - rr * (int32_t) a.ld0;
               if (ipn == (int32_t) ip) { more_same_parent = true; continue; }
               deg_more++;
-              const int z2 = a.z[nb];
+              const int z2 = a.fuse ? (int) __ldcg(a.z + nb) : (int) a.z[nb];
               cp_more += z2 == zk;
               cn_more += z2 == zn;
             }
@@ -305,19 +339,18 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           }
           __syncwarp();
         }
-        if (ADAPT && active && r == 0) a.nacc[ip] = nacc_new;
       }
-      // ---- stage sqrt(w) y and fold the statistics of this pass -----------------------------------
-      {
-        const double sw = active ? sqrt(wj) : 0.0;
-#pragma unroll
-        for (int c = 0; c < D; c++) tile[c * kTileLd + tid] = active ? sw * y[c] : 0.0;
-        sws[tid] = sw;
-        wvs[tid] = active ? wj : 0.0;
-        zs[tid] = (uint8_t) (active ? zfinal : 255);
+      // ---- per-cluster sums with the final labels ---------------------------------------------------
+      zs[tid] = (uint8_t) (active ? zfinal : 255);
+      if (a.fuse && !a.stats_only && base + ppb >= count) {
+        // the labels of this segment are final (last pass): let the next colour class go before folding the statistics
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.done + my_colour, 1u);
+      } else {
+        __syncthreads();
       }
-      __syncthreads();
-      tile_stats_mma<D>(ct, tile, zs, true, nh, warp, lane);
+      if (nh) tile_stats_mma<D>(ct, tile, zs, false, nh, warp, lane, nh);
       if (scalar_sums) tile_cluster_sums<D>(accP, P, q, tile, sws, wvs, zs, tid);
       __syncthreads();
     }

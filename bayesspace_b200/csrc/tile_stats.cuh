@@ -66,15 +66,19 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 // register as the A fragment of row-tile j, so NT loads feed all the DMMAs of a group of 4 spots.
 template <int D>
 __device__ __forceinline__ void tile_stats_mma(double *cacc, const double *tile, const uint8_t *zs, bool do_pairs, int nh,
-                                               int warp, int lane) {
+                                               int warp, int lane, int nh_layout = -1) {
+  // nh: label tiles folded by THIS call; nh_layout: label tiles the accumulator area was laid out for (a caller may
+  // fold the second moments and the label tiles in separate calls)
   constexpr int NT = TileGeom<D>::NT, NTILES = TileGeom<D>::NTILES, NW = kBlock / 32;
-  const int NFRAG = stats_frags(D, nh);
+  const int NFRAG = stats_frags(D, nh_layout < 0 ? nh : nh_layout);
   // The output tiles live in shared memory between tiles (warp-private, 2 doubles per lane and tile): they are
   // only in registers while the DMMAs run, which keeps the per-spot phase of the kernel below 128 registers.
   double2 *mine = reinterpret_cast<double2 *>(cacc + (size_t) warp * NFRAG * 64 + (lane >> 2) * 8 + 2 * (lane & 3));
   double C[NTILES][2], CH[NT][2][2];
+  if (do_pairs) {
 #pragma unroll
-  for (int t = 0; t < NTILES; t++) { const double2 v = mine[t * 32]; C[t][0] = v.x; C[t][1] = v.y; }
+    for (int t = 0; t < NTILES; t++) { const double2 v = mine[t * 32]; C[t][0] = v.x; C[t][1] = v.y; }
+  }
 #pragma unroll
   for (int i = 0; i < NT; i++)
 #pragma unroll
@@ -98,6 +102,7 @@ __device__ __forceinline__ void tile_stats_mma(double *cacc, const double *tile,
 #pragma unroll
         for (int j = i; j < NT; j++) dmma_m8n8k4(C[tix++], f[i], f[j]);
     }
+    if (nh == 0) continue;
     const int zt = zs[t0 + (lane & 3)];
     const double swt = swrow[t0];
     const double h0 = zt == kc ? swt : 0.0;
@@ -109,8 +114,10 @@ __device__ __forceinline__ void tile_stats_mma(double *cacc, const double *tile,
       for (int i = 0; i < NT; i++) dmma_m8n8k4(CH[i][1], f[i], h1);
     }
   }
+  if (do_pairs) {
 #pragma unroll
-  for (int t = 0; t < NTILES; t++) mine[t * 32] = make_double2(C[t][0], C[t][1]);
+    for (int t = 0; t < NTILES; t++) mine[t * 32] = make_double2(C[t][0], C[t][1]);
+  }
 #pragma unroll
   for (int i = 0; i < NT; i++)
 #pragma unroll
