@@ -274,6 +274,9 @@ struct bsb200_chain {
   int comm_rc = 0;               // first NCCL failure seen while enqueuing (reported by the next sync point)
   double *gsum_p = nullptr;      // shard sums: own buffer, or the exported window of the peer transport
   SweepMaps maps;                // TMA descriptors of Y / ell / orig
+  bool fuse_colours = false;     // small single-GPU chains: all colour classes in one launch (ColourFuse)
+  DevBuf<int32_t> colour_seg_start;
+  DevBuf<uint32_t> colour_done;
   bool fused_halo = false;       // peer transport + k_sweep_fast: the sweep launches exchange the halos themselves
   std::vector<int> nbound;       // per colour: boundary segments (first in the launch list)
   DevBuf<uint32_t> halo_done;    // per colour: finished boundary segments of the running launch
@@ -305,6 +308,10 @@ struct bsb200_chain {
     a.iter = iter.p; a.iter_add = iter_add;
     a.key0 = (uint32_t) seed; a.key1 = (uint32_t) (seed >> 32);
     a.gamma = gamma; a.flags = flags | sweep_flags; a.err = err.p;
+    if (fuse_colours && colour < 0 && flags == 0) {
+      a.cfuse.on = 1; a.cfuse.ncol = ord.ncol;
+      a.cfuse.colour_seg_start = colour_seg_start.p; a.cfuse.done = colour_done.p;
+    }
     if (fused_halo && colour >= 0 && !(flags & SW_STATS_ONLY)) {
       a.halo.legs = comm.halo_legs + (size_t) colour * (size_t) (world() - 1);
       a.halo.nlegs = comm.halo_leg_count[(size_t) colour];
@@ -327,6 +334,7 @@ struct bsb200_chain {
     a.iter = iter.p; a.nrep = nrep; a.thin = thin; a.plogLik = plogLik.p;
     a.snap_mu = snap_mu.p; a.snap_lambda = snap_lambda.p;
     a.finalize_only = finalize_only; a.precision_form = 0; a.err = err.p;
+    if (fuse_colours) { a.zero_counters = colour_done.p; a.n_zero = ord.ncol; }
     return a;
   }
   // level 1 of the statistics fold on the shards this rank owns, allgather of the shard sums, k_param
@@ -372,6 +380,10 @@ struct bsb200_chain {
   }
   void enqueue_iteration(cudaStream_t s) {
     enqueue_reduce_and_param(false, s);
+    if (fuse_colours) {   // every colour class in one launch, ordered by in-kernel counters
+      enqueue_sweep(-1, 0, 0, s);
+      return;
+    }
     for (int c = 0; c < ord.ncol; c++) {
       enqueue_sweep(c, 0, 0, s);
       enqueue_halo(c, s);
@@ -760,6 +772,19 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if (encode_sweep_maps(ch->Y.p, ch->ld, d, ch->ell.p, maxdeg, ch->orig.p, &ch->maps, &msg))
       return fail(BSB200_ERR_CUDA, "cannot encode the TMA descriptors (%s)", msg);
     ch->have_maps = true;
+  }
+  {   // all colour classes in one launch when every CTA of that launch is resident at once
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device));
+    static const bool off = std::getenv("BSB200_NO_FUSED_COLOURS") != nullptr;
+    ch->fuse_colours = !off && world == 1 && ncol > 1 && K.sweep_fast && !ch->vvv && q <= kFastMaxQ &&
+                       !std::getenv("BSB200_NO_FAST_SWEEP") && (int64_t) ord.seg_begin.size() <= (int64_t) sms * (d <= 24 ? 2 : 1);
+    if (ch->fuse_colours) {
+      if ((rc = upload(ch->colour_seg_start, ord.colour_seg_start.data(), ord.colour_seg_start.size(), s)) ||
+          (rc = ch->colour_done.alloc((size_t) ncol)))
+        return rc;
+      CK(cudaMemsetAsync(ch->colour_done.p, 0, sizeof(uint32_t) * ncol, s));
+    }
   }
   mark("buffers");
   // ---- the configuration must fit the shared memory of one CTA (sweep: per-cluster parameter blocks + tiles;

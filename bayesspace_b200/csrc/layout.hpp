@@ -108,6 +108,17 @@ struct HaloFuse {
   unsigned long long timeout_ns;
 };
 
+// All colour classes of a SMALL chain in one launch (every CTA resident at once, one segment per CTA): everything
+// that does not depend on the neighbours' labels -- random numbers, quadratic form, t-weight -- runs at once; a CTA
+// of colour class c then waits until all segments of class c - 1 have published their labels (done[c - 1], reset by
+// k_param every iteration), gathers its neighbours' labels and finishes.  Saves ncol - 1 launch latencies per iteration
+// where the launches are latency bound (Visium: 13 CTAs per colour class).
+struct ColourFuse {
+  int on, ncol;
+  const int32_t *colour_seg_start;   // ncol + 1 offsets into the (colour-major) launch list
+  uint32_t *done;                    // ncol counters
+};
+
 struct SweepArgs {
   const SweepMaps *maps;      // host pointer: TMA descriptors of Y / ell / orig (k_sweep_fast), may be null
   const double *Y;
@@ -131,6 +142,7 @@ struct SweepArgs {
   double gamma;
   uint32_t flags;
   int *err;
+  ColourFuse cfuse;           // all colour classes in one launch (small chains, k_sweep_fast)
   HaloFuse halo;              // fused halo exchange (k_sweep_fast, peer transport); nlegs == 0 otherwise
   int32_t *dry_znew;          // dry-run outputs, original spot order
   double *dry_w, *dry_hp, *dry_hn, *dry_prob;
@@ -166,6 +178,8 @@ struct ParamArgs {
   double n0;                    // parents (deconv)
   double *snap_mu;              // nsnap * q*d
   double *snap_lambda;          // nsnap * nl*d*d
+  uint32_t *zero_counters;      // counters k_param resets for the coming sweep (ColourFuse::done), or nullptr
+  int n_zero;
   int finalize_only;            // reduce + plogLik only (after the last iteration)
   int precision_form;           // 1: density in precision form (deconv): M = Lambda, no Sigma chain
   int *err;

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
   double *MB = MA + (size_t) batch * dd, *MC = MB + (size_t) batch * dd, *MD = MC + (size_t) batch * dd;
   const double LOG2PI = 1.8378770664093454835606594728112;
   if (tid == 0) s_ok = 1;
+  if (a.zero_counters && tid < a.n_zero) a.zero_counters[tid] = 0u;
   BSB_T(0);
 
   // ---- (0) deterministic two-level reduction of the segment partials ---------------------------

@@ -155,7 +155,7 @@ __device__ __forceinline__ void dot3(const double (&y)[D], const double *__restr
 
 constexpr int kNbInline = 6;   // neighbour slots handled in the straight-line part (hex lattice degree); the rest in a loop
 
-template <int D, bool TDIST, int NH, bool LEAN>
+template <int D, bool TDIST, int NH, bool LEAN, bool FUSEC>
 __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     k_sweep_fast(const __grid_constant__ SweepArgs a, const __grid_constant__ SweepMaps maps) {
   extern __shared__ __align__(1024) unsigned char smdyn[];
@@ -245,6 +245,9 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     const int nsub = (count + 31) >> 5;
     // fused halo exchange (HaloFuse, layout.hpp): a boundary segment first makes sure the neighbours' labels of the
     // previous colour phase have landed in this rank's ghost slots
+    int my_colour = 0;
+    if (FUSEC)
+      while (my_colour + 1 < a.cfuse.ncol && seg >= a.cfuse.colour_seg_start[my_colour + 1]) my_colour++;
     const bool bseg = a.halo.nlegs > 0 && seg < a.halo.nbound && !stats_only;
     if (bseg) {
       if (tid == 0) {
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         const uint32_t og = (uint32_t) worig[cur * 32 + lane];
         // neighbour labels: issue the gathers first, they are the longest latency of the spot
         int zu[kNbInline];
-        {
+        if (!FUSEC) {
           const int32_t *ellrow = well + cur * ell_rows * 32 + lane;
 #pragma unroll
           for (int e = 0; e < kNbInline; e++) {
@@ -329,6 +332,32 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         }
         const double lin_p = s_c[zk] - 2.0 * dp;
         const double lin_n = s_c[zn] - 2.0 * dn;
+        if (TDIST && FUSEC) wj = rng_gamma_spot(key, og, it, w_alpha, scale, x0, u_sq, s_logtab);
+        if (FUSEC) {
+          // one launch for all colour classes: everything above is independent of the neighbours; their labels are
+          // final once every segment of the previous class has published (counter reset by k_param each iteration)
+          if (my_colour > 0) {
+            if (lane == 0) {
+              const uint32_t target = (uint32_t) (a.cfuse.colour_seg_start[my_colour] - a.cfuse.colour_seg_start[my_colour - 1]);
+              const uint32_t *flag = a.cfuse.done + (my_colour - 1);
+              const unsigned long long t0 = global_ns();
+              uint32_t v;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (v >= target || *(volatile int *) a.err) break;
+                __nanosleep(32);
+                if (global_ns() - t0 > 20ull * 1000 * 1000 * 1000) { atomicCAS(a.err, 0, BSB_DEVERR_PEER_TIMEOUT); break; }
+              } while (true);
+            }
+            __syncwarp();
+          }
+          const int32_t *ellrow = well + cur * ell_rows * 32 + lane;
+#pragma unroll
+          for (int e = 0; e < kNbInline; e++) {
+            const int32_t nb = e < ell_rows ? ellrow[e * 32] : -1;
+            zu[e] = nb >= 0 ? (int) __ldcg(a.z + nb) : -1;
+          }
+        }
         int deg = 0, cp = 0, cn = 0;
 #pragma unroll
         for (int e = 0; e < kNbInline; e++) {
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         for (int e = kNbInline; e < ell_rows; e++) {   // general graphs with more than 6 neighbours
           const int32_t nb = well[(cur * ell_rows + e) * 32 + lane];
           if (nb >= 0) {
-            const int z2 = a.z[nb];
+            const int z2 = FUSEC ? (int) __ldcg(a.z + nb) : (int) a.z[nb];
             deg++;
             cp += z2 == zk;
             cn += z2 == zn;
@@ -347,7 +376,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         }
         const double ps = s_pot[deg];
         const double pot_p = ps * cp, pot_n = ps * cn;
-        if (TDIST) wj = rng_gamma_spot(key, og, it, w_alpha, scale, x0, u_sq, s_logtab);
+        if (TDIST && !FUSEC) wj = rng_gamma_spot(key, og, it, w_alpha, scale, x0, u_sq, s_logtab);
         // y^T M y and (d/2) log w_j are common to both labels: they only enter plogLik (statistics, lw)
         const double delta = (pot_n - pot_p) - 0.5 * wj * (lin_n - lin_p);
         const double hp_part = pot_p - 0.5 * wj * lin_p;
@@ -463,7 +492,9 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
 #pragma unroll
         for (int h = 0; h < NH; h++) mine[(NTILES + h * NT + i) * 32] = make_double2(CH[i][h][0], CH[i][h][1]);
     }
+    if (FUSEC) __threadfence();                   // this segment's labels, before the barrier below
     block_reduce3(hp_acc, nacc, lws, red, tid);   // contains a __syncthreads()
+    if (FUSEC && tid == 0) atomicAdd(a.cfuse.done + my_colour, 1u);   // ... are final: the next colour class may read them
     if (tid == 0) {
       acc[a.SL.hp] = hp_acc + halfD * lws;
       acc[a.SL.nacc] = nacc;
@@ -523,12 +554,12 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   }
 }
 
-template <bool TDIST, int NH, bool LEAN>
+template <bool TDIST, int NH, bool LEAN, bool FUSEC>
 int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   constexpr int D = BSB_D;
   const FastSmem L = fast_smem_layout(D, a.PL.q, a.SL.E, TDIST, NH, a.maxdeg);
   static size_t granted[64] = {};
-  const cudaError_t e = ensure_dynamic_smem(k_sweep_fast<D, TDIST, NH, LEAN>, L.bytes, granted);
+  const cudaError_t e = ensure_dynamic_smem(k_sweep_fast<D, TDIST, NH, LEAN, FUSEC>, L.bytes, granted);
   if (e != cudaSuccess) return (int) e;
   // Persistent launch: at most as many CTAs as the device holds at once, each walking its segments (seg = blockIdx.x,
   // + gridDim.x, ...).  The per-CTA set-up (parameter staging, logarithm table, barrier initialisation) is then paid
@@ -539,14 +570,14 @@ int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   int resident = dev >= 0 && dev < 64 ? slots[dev] : 0;
   if (!resident) {
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH, LEAN>, kBlock, L.bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH, LEAN, FUSEC>, kBlock, L.bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     resident = per_sm > 0 && sms > 0 ? per_sm * sms : grid;
     if (dev >= 0 && dev < 64) slots[dev] = resident;   // for the largest q seen first; smaller q only fit better
   }
   static const bool persistent = std::getenv("BSB200_NO_PERSISTENT_SWEEP") == nullptr;
-  if (persistent && grid > resident) grid = resident;
-  k_sweep_fast<D, TDIST, NH, LEAN><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
+  if (persistent && grid > resident && !FUSEC) grid = resident;   // FUSEC: the caller made sure every CTA is resident
+  k_sweep_fast<D, TDIST, NH, LEAN, FUSEC><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
   return 0;
 }
 
@@ -554,12 +585,15 @@ int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
 void launch_fast(int tdist, const SweepArgs &a, int grid, cudaStream_t s) {
   const int nh = (a.PL.q + 7) / 8;
   const bool lean = !(a.flags & (SW_STATS_ONLY | SW_DRY));
-  if (lean) {
-    if (tdist) { if (nh == 1) launch_fast_t<true, 1, true>(a, grid, s); else launch_fast_t<true, 2, true>(a, grid, s); }
-    else { if (nh == 1) launch_fast_t<false, 1, true>(a, grid, s); else launch_fast_t<false, 2, true>(a, grid, s); }
+  if (lean && a.cfuse.on) {
+    if (tdist) { if (nh == 1) launch_fast_t<true, 1, true, true>(a, grid, s); else launch_fast_t<true, 2, true, true>(a, grid, s); }
+    else { if (nh == 1) launch_fast_t<false, 1, true, true>(a, grid, s); else launch_fast_t<false, 2, true, true>(a, grid, s); }
+  } else if (lean) {
+    if (tdist) { if (nh == 1) launch_fast_t<true, 1, true, false>(a, grid, s); else launch_fast_t<true, 2, true, false>(a, grid, s); }
+    else { if (nh == 1) launch_fast_t<false, 1, true, false>(a, grid, s); else launch_fast_t<false, 2, true, false>(a, grid, s); }
   } else {
-    if (tdist) { if (nh == 1) launch_fast_t<true, 1, false>(a, grid, s); else launch_fast_t<true, 2, false>(a, grid, s); }
-    else { if (nh == 1) launch_fast_t<false, 1, false>(a, grid, s); else launch_fast_t<false, 2, false>(a, grid, s); }
+    if (tdist) { if (nh == 1) launch_fast_t<true, 1, false, false>(a, grid, s); else launch_fast_t<true, 2, false, false>(a, grid, s); }
+    else { if (nh == 1) launch_fast_t<false, 1, false, false>(a, grid, s); else launch_fast_t<false, 2, false, false>(a, grid, s); }
   }
 }
 

@@ -307,7 +307,21 @@ def deconv_workload(B, device, peak, with_cpu):
     out = B.iterate_deconv(*args(iters + 1), seed=3, device=device, keep_Y=False, mean_from=1)
     ms = out["_info"]["device_ms"]
     bytes_per = 16.0 * w.d + 8.0 * w.d / dc["subspots"] + 8 + 4 * 3 + 16
-    res = {"config": {"workload": "C3: iterate_deconv, 4,992 Visium spots x 6 subspots = 29,952 subspots, t model, q=7, "
+    achieved = bytes_per * dc["n"] * iters / (ms * 1e-3) / 1e9
+    # Robust Adaptive Metropolis variant (jitter.scale = 0): + 2 * 8 * d(d+1)/2 bytes per subspot-update (RAM factors)
+    a2 = list(args(501))
+    a2[15] = 0.0
+    out2 = B.iterate_deconv(*a2, seed=3, device=device, keep_Y=False)
+    ms2 = out2["_info"]["device_ms"]
+    res = {"roofline": {"bound": "hbm", "kernel": "k_deconv<%d, fixed jitter> (whole iteration: k_param + one launch for all "
+                        "colour classes)" % w.d, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "algorithmic_bytes_per_subspot_update": bytes_per,
+                        "formula": "16d (Y read + write) + 8d/S (parent row) + 8 (z) + 4*deg + 16 (w) bytes per subspot-update",
+                        "note": "3.6 MB of state: resident in L2, the iteration is latency bound (84 CTAs per colour class, "
+                                "one warp per SMSP); microseconds per iteration is the meaningful figure"},
+           "adaptive": {"us_per_iteration": 1e3 * ms2 / 500, "Ychange_mean": float(np.nanmean(out2["Ychange"])),
+                        "algorithmic_bytes_per_subspot_update": bytes_per + 2 * 8 * w.d * (w.d + 1) / 2},
+           "config": {"workload": "C3: iterate_deconv, 4,992 Visium spots x 6 subspots = 29,952 subspots, t model, q=7, "
                                   "d=15, jitter.scale=5 (fixed proposal)", "n_subspots": dc["n"]},
            "subspot_updates_per_s": dc["n"] * iters / (ms * 1e-3), "sweeps_per_s": iters / (ms * 1e-3),
            "us_per_iteration": 1e3 * ms / iters, "Ychange_mean": float(np.nanmean(out["Ychange"])),
