@@ -611,7 +611,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
   const size_t Emax = (size_t) std::max(SL_run.E, SL_init.E);
   if (ch->comm.peer()) {   // labels, receive list and shard sums live in the arena the peers map
-    if ((rc = ch->comm.alloc_arena((size_t) ch->ld, ch->halo.recv_pos.size(), (size_t) G * Emax, s))) return rc;
+    if ((rc = ch->comm.alloc_arena((size_t) ch->ld + kSweepPad, ch->halo.recv_pos.size(), (size_t) G * Emax, s))) return rc;
     ch->z.adopt(ch->comm.z(), (size_t) ch->ld);
     ch->recv_pos.adopt(ch->comm.recv_pos(), ch->halo.recv_pos.size());
   }
@@ -630,7 +630,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     // neighbour ids in internal order (ELL, -1 padded), initial labels and original ids, filled by host threads
     const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;
     std::unique_ptr<int32_t[]> ell(new int32_t[ell_rows * ldp + kSweepPad]);
-    std::unique_ptr<uint8_t[]> z0(new uint8_t[ldp]);
+    // z[ld ..] = 255: the label that matches no cluster, read through padding entries of the neighbour lists
+    std::unique_ptr<uint8_t[]> z0(new uint8_t[ldp + kSweepPad]);
+    std::memset(z0.get() + ldp, 255, (size_t) kSweepPad);
     std::unique_ptr<int32_t[]> origp(new int32_t[ldp + kSweepPad]);
     parallel_for((int64_t) ldp, [&](int64_t i0, int64_t i1, int) {
       for (int64_t i = i0; i < i1; i++) {
@@ -659,8 +661,8 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
       origp[(size_t) n_pos + gi] = plan.ghosts[gi];
     }
     if ((rc = upload(ch->ell, ell.get(), ell_rows * ldp + kSweepPad, s))) return rc;
-    if (ch->comm.peer()) CK(cudaMemcpyAsync(ch->z.p, z0.get(), ldp, cudaMemcpyHostToDevice, s));
-    else if ((rc = upload(ch->z, z0.get(), ldp, s))) return rc;
+    if (ch->comm.peer()) CK(cudaMemcpyAsync(ch->z.p, z0.get(), ldp + kSweepPad, cudaMemcpyHostToDevice, s));
+    else if ((rc = upload(ch->z, z0.get(), ldp + kSweepPad, s))) return rc;
     if ((rc = upload(ch->orig, origp.get(), ldp + kSweepPad, s))) return rc;
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }

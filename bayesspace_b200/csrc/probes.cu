@@ -119,7 +119,7 @@ int bsb200_eval_suffstats(int32_t device, const double *Y, int64_t n, int32_t d,
       (rc = dybar.alloc((size_t) d)) || (rc = dpart.alloc((size_t) ord.nslots * SL.E)) ||
       (rc = dgsum.alloc((size_t) ord.ngroups * SL.E)) || (rc = dstats.alloc((size_t) SL.E)) ||
       (rc = dmu.alloc((size_t) q * d)) || (rc = dS.alloc((size_t) nl * d * d)) || (rc = dparams.alloc((size_t) PL.total)) ||
-      (rc = dplog.alloc(4)) || (rc = dz.alloc((size_t) ld)) || (rc = dorig.alloc((size_t) ld + kSweepPad)) ||
+      (rc = dplog.alloc(4)) || (rc = dz.alloc((size_t) ld + kSweepPad)) || (rc = dorig.alloc((size_t) ld + kSweepPad)) ||
       (rc = dsb.alloc(ord.seg_begin.size())) || (rc = dsc.alloc(ord.seg_begin.size())) ||
       (rc = dss.alloc(ord.seg_begin.size())) || (rc = dgs.alloc(ord.group_start.size())) || (rc = diter.alloc(1)) ||
       (rc = derr.alloc(1)))

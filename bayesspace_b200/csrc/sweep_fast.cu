@@ -38,7 +38,11 @@
 namespace bsb {
 namespace {
 
-constexpr int kWarps = kBlock / 32;
+#ifndef BSB_FAST_WARPS
+#define BSB_FAST_WARPS 4
+#endif
+constexpr int kWarps = BSB_FAST_WARPS;        // warps (independent workers) per CTA of k_sweep_fast
+constexpr int kFBlock = 32 * kWarps;          // threads per CTA
 constexpr int kRowB = 128;   // bytes of one row of a Y box (16 spots) and of an ell / orig row (32 spots)
 
 // Shared-memory carve-up (byte offsets; the per-warp areas start at a 1024-byte boundary, which SWIZZLE_128B needs
@@ -92,7 +96,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       : "memory");
 }
 
-constexpr int fast_min_blocks(int D) { return D <= 16 ? 4 : (D <= 24 ? 3 : 2); }
+#ifdef BSB_FAST_MINB   // tuning experiments
+constexpr int fast_min_blocks(int D) { return D <= 16 ? BSB_FAST_MINB : (D <= 24 ? BSB_FAST_MINB - 1 : 1); }
+#else
+constexpr int fast_min_blocks(int D) { return (D <= 16 ? 16 : (D <= 24 ? 12 : 8)) / kWarps; }   // 16 / 12 / 8 warps per SM
+#endif
 // The cluster sums of label-uniform sub-tiles come from the second moments' constant-row column (below) when the
 // per-warp accumulators fit next to four resident CTAs; larger d keep the shared memory for occupancy instead.
 __host__ __device__ constexpr bool fast_uniform_shortcut(int D) { return D <= 16; }
@@ -153,10 +161,27 @@ __device__ __forceinline__ void dot3(const double (&y)[D], const double *__restr
   dl = l0 + l1; dp = p0 + p1; dn = n0 + n1;
 }
 
+// Fixed-order CTA reduction of three per-thread scalars over kWarps warps; results valid on thread 0.
+__device__ __forceinline__ void block_reduce3_fast(double &x, double &y, double &z, double *red, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+  }
+  if ((tid & 31) == 0) { red[3 * (tid >> 5)] = x; red[3 * (tid >> 5) + 1] = y; red[3 * (tid >> 5) + 2] = z; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int wv = 0; wv < kWarps; wv++) { a += red[3 * wv]; b += red[3 * wv + 1]; c += red[3 * wv + 2]; }
+    x = a; y = b; z = c;
+  }
+}
+
 constexpr int kNbInline = 6;   // neighbour slots handled in the straight-line part (hex lattice degree); the rest in a loop
 
 template <int D, bool TDIST, int NH, bool LEAN, bool FUSEC>
-__global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
+__global__ void __launch_bounds__(kFBlock, fast_min_blocks(D))
     k_sweep_fast(const __grid_constant__ SweepArgs a, const __grid_constant__ SweepMaps maps) {
   extern __shared__ __align__(1024) unsigned char smdyn[];
   constexpr int NP = D * (D + 1) / 2, RS = D + (D & 1) + 2;   // RS = 2 (mod 16) doubles: rows of different clusters start in different banks
@@ -188,26 +213,26 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
   if (*a.err) return;
   if (!stats_only) {
     const double *Pm = a.params;
-    for (int e = tid; e < q * RS; e += kBlock) {
+    for (int e = tid; e < q * RS; e += kFBlock) {
       const int k = e / RS, cc = e - k * RS;
       s_g[e] = cc < D ? Pm[a.PL.g + k * D + cc] : 0.0;
       if (TDIST) s_gL[e] = cc < D ? Pm[a.PL.gL + k * D + cc] : 0.0;
     }
-    for (int e = tid; e < q; e += kBlock) {
+    for (int e = tid; e < q; e += kFBlock) {
       s_c[e] = Pm[a.PL.c + e];
       if (TDIST) s_cL[e] = Pm[a.PL.cL + e];
     }
     if (TDIST) {   // packed Lambda, permuted from k_param's row-major order to column-major (quadform_cols)
-      for (int e = tid; e < NP; e += kBlock) {
+      for (int e = tid; e < NP; e += kFBlock) {
         int pa, pb;
         pair_from_index(e, D, pa, pb);
         s_PL[colpacked_index(pa, pb)] = Pm[a.PL.PL + e];
       }
       if (tid == 0 && (NP & 1)) s_PL[NP] = 0.0;
     }
-    for (int e = tid; e <= kMaxDeg; e += kBlock) s_pot[e] = e ? a.gamma / e * 2 : 0.0;   // (gamma / |N_j|) * 2 as at :289
+    for (int e = tid; e <= kMaxDeg; e += kFBlock) s_pot[e] = e ? a.gamma / e * 2 : 0.0;   // (gamma / |N_j|) * 2 as at :289
     if (TDIST)
-      for (int e = tid; e < 128; e += kBlock) log_table_entry(e, s_logtab[e]);
+      for (int e = tid; e < 128; e += kFBlock) log_table_entry(e, s_logtab[e]);
   }
   // constant rows of the four boxes: row D = 1 (its products give n_k and the sum of weights), rows beyond = 0
   auto init_const_rows = [&]() {
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       }
       __syncthreads();
     }
-    for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
+    for (int e = tid; e < E; e += kFBlock) acc[e] = 0.0;
     if (fast_uniform_shortcut(D))
       for (int e = lane; e < q * DP; e += 32) skacc[e] = 0.0;
     double hp_acc = 0.0, nacc = 0.0, lw_m = 1.0;
@@ -301,13 +326,16 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
       } else {
         const uint32_t og = (uint32_t) worig[cur * 32 + lane];
         // neighbour labels: issue the gathers first, they are the longest latency of the spot
-        int zu[kNbInline];
+        // Padding entries (-1) read z[ld] = 255, a label no cluster has: the loads carry no select after them, so the
+        // in-order issue does not stall on them before the independent work below has been issued
+        int zu[kNbInline], deg = 0;
         if (!FUSEC) {
           const int32_t *ellrow = well + cur * ell_rows * 32 + lane;
 #pragma unroll
           for (int e = 0; e < kNbInline; e++) {
             const int32_t nb = e < ell_rows ? ellrow[e * 32] : -1;
-            zu[e] = nb >= 0 ? (int) a.z[nb] : -1;
+            deg += nb >= 0;
+            zu[e] = a.z[nb >= 0 ? (int64_t) nb : a.ld];
           }
         }
         // randomness: depends on nothing but (spot, iteration)
@@ -355,13 +383,13 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
 #pragma unroll
           for (int e = 0; e < kNbInline; e++) {
             const int32_t nb = e < ell_rows ? ellrow[e * 32] : -1;
-            zu[e] = nb >= 0 ? (int) __ldcg(a.z + nb) : -1;
+            deg += nb >= 0;
+            zu[e] = __ldcg(a.z + (nb >= 0 ? (int64_t) nb : a.ld));
           }
         }
-        int deg = 0, cp = 0, cn = 0;
+        int cp = 0, cn = 0;
 #pragma unroll
         for (int e = 0; e < kNbInline; e++) {
-          deg += zu[e] >= 0;
           cp += zu[e] == zk;
           cn += zu[e] == zn;
         }
@@ -493,14 +521,14 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         for (int h = 0; h < NH; h++) mine[(NTILES + h * NT + i) * 32] = make_double2(CH[i][h][0], CH[i][h][1]);
     }
     if (FUSEC) __threadfence();                   // this segment's labels, before the barrier below
-    block_reduce3(hp_acc, nacc, lws, red, tid);   // contains a __syncthreads()
+    block_reduce3_fast(hp_acc, nacc, lws, red, tid);   // contains a __syncthreads()
     if (FUSEC && tid == 0) atomicAdd(a.cfuse.done + my_colour, 1u);   // ... are final: the next colour class may read them
     if (tid == 0) {
       acc[a.SL.hp] = hp_acc + halfD * lws;
       acc[a.SL.nacc] = nacc;
     }
     if (do_pairs)
-      for (int p = tid; p < NP; p += kBlock) {
+      for (int p = tid; p < NP; p += kFBlock) {
         int pa, pb;
         pair_from_index(p, D, pa, pb);
         const int i = pa >> 3, jj = pb >> 3;
@@ -510,7 +538,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         for (int w = 0; w < kWarps; w++) s += cfold[(size_t) w * fold_stride + t * 64 + (pa & 7) * 8 + (pb & 7)];
         acc[a.SL.T + p] = s;
       }
-    for (int e = tid; e < q * (D + 1); e += kBlock) {   // (cluster k, row r): r < D -> s_k[r], r == D -> n_k
+    for (int e = tid; e < q * (D + 1); e += kFBlock) {   // (cluster k, row r): r < D -> s_k[r], r == D -> n_k
       const int k = e / (D + 1), r = e - k * (D + 1);
       const int t = NTILES + (k >> 3) * NT + (r >> 3);
       double s = 0.0;
@@ -525,7 +553,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
     }
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
-    for (int e = tid; e < E; e += kBlock) out[e] = acc[e];
+    for (int e = tid; e < E; e += kFBlock) out[e] = acc[e];
     if (bseg && !dry) {
       // the CTA that completes the LAST boundary segment of this launch pushes the boundary labels of this colour to
       // the neighbours and releases their flags; the interior segments of the launch are still running
@@ -537,7 +565,7 @@ __global__ void __launch_bounds__(kBlock, fast_min_blocks(D))
         __threadfence();
         for (int l = 0; l < a.halo.nlegs; l++) {
           const HaloLeg leg = a.halo.legs[l];
-          for (int k = leg.s0 + tid; k < leg.s1; k += kBlock) leg.peer_z[a.halo.send_dst[k]] = __ldcg(a.z + a.halo.send_pos[k]);
+          for (int k = leg.s0 + tid; k < leg.s1; k += kFBlock) leg.peer_z[a.halo.send_dst[k]] = __ldcg(a.z + a.halo.send_pos[k]);
         }
         __threadfence_system();
         __syncthreads();
@@ -570,14 +598,14 @@ int launch_fast_t(const SweepArgs &a, int grid, cudaStream_t s) {
   int resident = dev >= 0 && dev < 64 ? slots[dev] : 0;
   if (!resident) {
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH, LEAN, FUSEC>, kBlock, L.bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fast<D, TDIST, NH, LEAN, FUSEC>, kFBlock, L.bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     resident = per_sm > 0 && sms > 0 ? per_sm * sms : grid;
     if (dev >= 0 && dev < 64) slots[dev] = resident;   // for the largest q seen first; smaller q only fit better
   }
   static const bool persistent = std::getenv("BSB200_NO_PERSISTENT_SWEEP") == nullptr;
   if (persistent && grid > resident && !FUSEC) grid = resident;   // FUSEC: the caller made sure every CTA is resident
-  k_sweep_fast<D, TDIST, NH, LEAN, FUSEC><<<grid, kBlock, L.bytes, s>>>(a, *a.maps);
+  k_sweep_fast<D, TDIST, NH, LEAN, FUSEC><<<grid, kFBlock, L.bytes, s>>>(a, *a.maps);
   return 0;
 }
 
