@@ -177,8 +177,19 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
   double *const gsum = a.gsum + (a.gepoch ? (size_t) (*a.gepoch & 1u) * a.gsum_stride : (size_t) 0);
   for (int idx = tid; !a.gsum_ready && idx < E * a.ngroups; idx += nt) {
     const int e = idx % E, g = idx / E;
+    // slots of a shard folded in slot order (fixed association); loads issued 8 at a time ahead of the adds
+    const int s0 = a.group_start[g], s1 = a.group_start[g + 1];
+    const double *pp = a.partials + e;
     double s = 0.0;
-    for (int slot = a.group_start[g]; slot < a.group_start[g + 1]; slot++) s += a.partials[(size_t) slot * E + e];
+    int slot = s0;
+    for (; slot + 8 <= s1; slot += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldcg(pp + (size_t) (slot + u) * E);
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += v[u];
+    }
+    for (; slot < s1; slot++) s += __ldcg(pp + (size_t) slot * E);
     gsum[(size_t) g * E + e] = s;
   }
   __syncthreads();
@@ -201,8 +212,10 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
   __syncthreads();
   BSB_T(1);
 
-  // plogLik of the sweep that just finished (uses the parameters of that sweep, still in P)
-  if (it_prev >= 1u && warp == 0) {
+  // plogLik of the sweep that just finished (uses the parameters of that sweep, still in P: the density matrix and its
+  // log-determinant are only replaced in phase (2)).  One warp; when a warp is idle during the factorisations of the mu
+  // phase (q <= 7) it runs there, off the critical path.
+  auto close_plogLik = [&]() {
     double pl;
     if (!a.vvv) {
       const double *T = a.SL.nlT ? st + a.SL.T : a.T_fixed;
@@ -218,7 +231,9 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       a.plogLik[it_prev] = pl;
       if (a.ychange) a.ychange[it_prev] = st[a.SL.nacc] / a.n0;   // src/cluster.cpp:1055
     }
-  }
+  };
+  const bool plog_late = !a.finalize_only && q <= 7 && D > 0;
+  if (it_prev >= 1u && warp == 0 && !plog_late) close_plogLik();
   if (a.finalize_only) return;
   if (*a.err) return;
   __syncthreads();
@@ -242,6 +257,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
         warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);            // MA = U
         warp_inv_upper_reg<D>(MA + b * dd, MB + b * dd, lane);    // MB = R = chol_upper(var)
       }
+      if (plog_late && k0 == 0 && warp == 7 && it_prev >= 1u) close_plogLik();   // the idle warp of this phase
       __syncthreads();
     } else {
       blk_revchol((int) (MA - sm), nb, d, &s_ok);
@@ -336,15 +352,23 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
     }
     __syncthreads();
     BSB_T(9);
-    if constexpr (D > 0) {
-#pragma unroll 1
-      for (int b = warp; b < nb; b += 8) warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);   // Lambda = rooti rooti^T
-      __syncthreads();
-    BSB_T(10);
-    } else {
-      blk_revchol((int) (MA - sm), nb, d, &s_ok);
-    }
     const bool q1 = (a.compat & BSB_COMPAT_Q1_BIT) && !a.precision_form;
+    // The factor of Lambda itself is only needed for quirk Q1 (M = rooti^T rooti).  Otherwise M = Lambda and the
+    // log-determinant term, sum log diag(rooti) = log det(Lambda) / 2, equals sum log diag(B) of Lambda = B^T B (MD).
+    if (q1) {
+      if constexpr (D > 0) {
+#pragma unroll 1
+        for (int b = warp; b < nb; b += 8) warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);   // Lambda = rooti rooti^T
+        __syncthreads();
+      } else {
+        blk_revchol((int) (MA - sm), nb, d, &s_ok);
+      }
+    } else {
+      for (int b = warp; b < nb; b += 8)
+        if (lane < d) MAT(MA, b, lane, lane) = MAT(MD, b, lane, lane);
+      __syncthreads();
+    }
+    BSB_T(10);
     for (int idx = tid; idx < nb * (int) dd; idx += nt) {   // density matrix M -> MD and packed into P
       const int b = idx / (int) dd, e = idx - b * (int) dd, i = e % d, j = e / d, kk = k0 + b;
       double s;
