@@ -190,9 +190,42 @@ __device__ __forceinline__ double log_tab(double u, const double2 *__restrict__ 
 }
 
 // First Box-Muller output from one Philox block, logarithm from the table.
+// Its two other factors, written out so that the sweep's straight-line block has neither the table loads of cospi()
+// nor the range checks and slow path of sqrt():
+// cos(2 pi u), u in (0, 1]: r = 2u - rint(2u) in [-1/2, 1/2], cos(2 pi u) = (-1)^rint(2u) cos(pi r), and cos(pi r) by
+// its Taylor polynomial in r^2 up to r^20 (first dropped term < 2e-17; absolute error ~3e-16, like cospi's).
+__device__ __forceinline__ double cos2pi_unit(double u) {
+  const double t = u + u, big = 6755399441055744.0;   // 1.5 * 2^52: t + big has rint(t) in its low bits
+  const double kb = t + big;
+  const double r = t - (kb - big);
+  const double s = r * r;
+  double p = 0x1.ef6e308d6d1c4p-29;
+  p = fma(p, s, -0x1.2a0c591af8314p-23);
+  p = fma(p, s, 0x1.20c62c2f2d7f5p-18);
+  p = fma(p, s, -0x1.b6e24f44b128fp-14);
+  p = fma(p, s, 0x1.f9d38a3763cc3p-10);
+  p = fma(p, s, -0x1.a6d1f2a204a8cp-6);
+  p = fma(p, s, 0x1.e1f506891babbp-3);
+  p = fma(p, s, -0x1.55d3c7e3cbffap+0);
+  p = fma(p, s, 0x1.03c1f081b5ac4p+2);
+  p = fma(p, s, -0x1.3bd3cc9be45dep+2);
+  p = fma(p, s, 1.0);
+  return __hiloint2double(__double2hiint(p) ^ (__double2loint(kb) << 31), __double2loint(p));
+}
+// sqrt(|a|) for |a| < 2^1000, |a| below 2^-1022 read as 2^-1022: reciprocal square root seed (2^-22), one coupled
+// Goldschmidt step and one correction, within an ulp.
+__device__ __forceinline__ double sqrt_small(double a) {
+  a = __hiloint2double(max(__double2hiint(a) & 0x7fffffff, 0x00100000), __double2loint(a));
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double g0 = a * r, h0 = 0.5 * r;
+  const double e = fma(-h0, g0, 0.5);
+  const double g = fma(g0, e, g0), h = fma(h0, e, h0);
+  return fma(fma(-g, g, a), h, g);
+}
 __device__ __forceinline__ double normal_from_block(uint4 o, const double2 *__restrict__ tab) {
   const double u0 = u53(o.x, o.y), u1 = u53(o.z, o.w);
-  return sqrt(-2.0 * log_tab(u0, tab)) * cospi(2.0 * u1);
+  return sqrt_small(-2.0 * log_tab(u0, tab)) * cos2pi_unit(u1);
 }
 
 // One Marsaglia-Tsang attempt for Gamma(shape >= 1): true when (x, u) is accepted, v3 = (1 + c x)^3.
