@@ -223,6 +223,14 @@ __device__ __forceinline__ double sqrt_small(double a) {
   const double g = fma(g0, e, g0), h = fma(h0, e, h0);
   return fma(fma(-g, g, a), h, g);
 }
+// 1 / x for normal x of moderate size (the t-weight's scale, x >= 2): reciprocal seed and two Newton steps, within an
+// ulp of the division without its range checks.
+__device__ __forceinline__ double rcp_moderate(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  return fma(r, fma(-x, r, 1.0), r);
+}
 __device__ __forceinline__ double normal_from_block(uint4 o, const double2 *__restrict__ tab) {
   const double u0 = u53(o.x, o.y), u1 = u53(o.z, o.w);
   return sqrt_small(-2.0 * log_tab(u0, tab)) * cos2pi_unit(u1);

@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(kFBlock, fast_min_blocks(D))
         if (TDIST) {
           // w_j ~ Gamma((d+4)/2, scale 2 / ((y-mu)^T Lambda (y-mu) + 4))   (:513-518)
           const double aL = quadform_cols<D>(y, s_PL);
-          scale = 2.0 / ((aL - 2.0 * bL + s_cL[zk]) + 4.0);
+          // 2 / (quadratic form + 4).  Measured on one box: the written-out reciprocal is 2.7 % faster at d = 20 and 2 %
+          // slower at d = 15, where its longer live ranges add spills at 128 registers
+          const double qf = aL - 2.0 * bL + s_cL[zk];
+          scale = D > 16 ? rcp_moderate(fma(0.5, qf, 2.0)) : 2.0 / (qf + 4.0);
         }
         const double lin_p = s_c[zk] - 2.0 * dp;
         const double lin_n = s_c[zn] - 2.0 * dn;

@@ -1,6 +1,10 @@
 import sys, time; sys.path.insert(0,'.')
 import numpy as np
 import bayesspace_b200 as B
+import os
+if os.environ.get('AB_LIB'):   # A/B of two builds on one box
+    import bayesspace_b200._lib as _L
+    _L.LIB_PATH = os.path.abspath(os.environ['AB_LIB'])
 import bench
 name = sys.argv[1]; iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 3
