@@ -49,6 +49,15 @@ __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, i
   return s;
 }
 
+// subspot position nb = rr * ld0 + ipn -> (rr, ipn) without the integer division: rr < S <= 32, so the single-precision
+// quotient is within one of the true one.
+__device__ __forceinline__ void split_subspot(int32_t nb, int32_t ld0, float inv_ld0, int32_t &rr, int32_t &ipn) {
+  rr = (int32_t) ((float) nb * inv_ld0);
+  ipn = nb - rr * ld0;
+  if (ipn < 0) { rr--; ipn += ld0; }
+  else if (ipn >= ld0) { rr++; ipn -= ld0; }
+}
+
 template <int D, bool ADAPT>
 __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -66,8 +75,11 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
   if (!a.stats_only) {
     const double *P = a.params;
+#pragma unroll 1
     for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
+#pragma unroll 1
     for (int e = tid; e < q; e += kBlock) s_cL[e] = P[a.PL.cL + e];
+#pragma unroll 1
     for (int e = tid; e < NP; e += kBlock) s_PL[e] = P[a.PL.PL + e];
   }
   const Key key{a.key0, a.key1};
@@ -79,6 +91,8 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   const int g = lane / S, r = lane - g * S;
   const bool lane_valid = g < gpw;
   const int glane0 = g * S;                        // first lane of this parent's group
+  const double inv_S = 1.0 / S;
+  const float inv_ld0 = 1.0f / (float) a.ld0;
   __syncthreads();
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
@@ -86,6 +100,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
     int my_colour = 0;
     if (a.fuse)
       while (my_colour + 1 < a.ncol && seg >= a.colour_seg_start[my_colour + 1]) my_colour++;
+#pragma unroll 1
     for (int e = tid; e < E; e += kBlock) acc[e] = 0.0;
     for (int e = tid; e < P * q * (D + 2); e += kBlock) accP[e] = 0.0;
     for (int e = tid; e < (kBlock / 32) * stats_frags(D, nh) * 64; e += kBlock) ct[e] = 0.0;
@@ -120,13 +135,19 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         for (int c = 0; c < (ADAPT ? D : 1); c++) v[c] = 0.0;
         // ---- jitter: rmvnorm(n, 0, I * jitter_scale) (:905-908), transformed by the RAM factor (:922-929)
         if (active) {
-#pragma unroll
-          for (int c = 0; c < D; c += 2) {
+          // One copy of the Box-Muller code instead of (D + 1) / 2: the loop is rolled and hands its pairs over through
+          // this thread's column of the staging tile, which is free until sqrt(w) y is staged below (row D, hit by the
+          // last pair when D is odd, is rewritten there).  The kernel runs a handful of warps per SM once per colour
+          // class: its time is instruction fetch as much as arithmetic, so code size is what counts here.
+#pragma unroll 1
+          for (int c2 = 0; c2 < (D + 1) / 2; c2++) {
             double n0v, n1v;
-            rng_normal2(key, P_ERR, sorig, it, (uint32_t) (c >> 1), n0v, n1v);
-            e[c] = a.err_sd * n0v;
-            if (c + 1 < D) e[c + 1] = a.err_sd * n1v;
+            rng_normal2(key, P_ERR, sorig, it, (uint32_t) c2, n0v, n1v);
+            tile[(2 * c2) * kTileLd + tid] = a.err_sd * n0v;
+            tile[(2 * c2 + 1) * kTileLd + tid] = a.err_sd * n1v;
           }
+#pragma unroll
+          for (int c = 0; c < D; c++) e[c] = tile[c * kTileLd + tid];
           if (ADAPT) {
 #pragma unroll
             for (int i = 0; i < D; i++) {
@@ -143,11 +164,18 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           for (int c = 0; c < D; c++) { usq += e[c] * e[c]; e[c] = v[c]; }
         }
         // ---- zero-sum constraint: subtract the mean over the parent's S subspots (:932-935)
+        {
+          double tot[D];
 #pragma unroll
-        for (int c = 0; c < D; c++) {
-          double tot = 0.0;
-          for (int rr = 0; rr < S; rr++) tot += __shfl_sync(0xffffffffu, e[c], glane0 + rr);
-          e[c] -= tot / S;
+          for (int c = 0; c < D; c++) tot[c] = 0.0;
+#pragma unroll 1
+          for (int rr = 0; rr < S; rr++) {
+            const int from = glane0 + rr;
+#pragma unroll
+            for (int c = 0; c < D; c++) tot[c] += __shfl_sync(0xffffffffu, e[c], from);
+          }
+#pragma unroll
+          for (int c = 0; c < D; c++) e[c] = fma(-tot[c], inv_S, e[c]);
         }
         // ---- log-ratio of the joint proposal (:941-956)
         double dl = 0.0, quad_old = 0.0, quad_new = 0.0, b_old = 0.0, b_new = 0.0;
@@ -167,6 +195,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           dl = -0.5 * wj * (quad_new - quad_old) - a.c * (pen_new - pen_old);
         }
         double tot = 0.0;
+#pragma unroll 1
         for (int rr = 0; rr < S; rr++) tot += __shfl_sync(0xffffffffu, dl, glane0 + rr);
         bool accY = false;
         if (active) {
@@ -278,7 +307,8 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
             const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
             if (nb >= 0) {
               deg++;
-              const int32_t rr = nb / (int32_t) a.ld0, ipn = nb - rr * (int32_t) a.ld0;
+              int32_t rr, ipn;
+              split_subspot(nb, (int32_t) a.ld0, inv_ld0, rr, ipn);
               if (ipn == (int32_t) ip) src[ee] = glane0 + rr;   // same parent: live label of that lane
               else zu[ee] = a.fuse ? (int) __ldcg(a.z + nb) : (int) a.z[nb];
             }
@@ -290,7 +320,8 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           for (int ee = kNbReg; ee < a.maxdeg; ee++) {
             const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
             if (nb >= 0) {
-              const int32_t rr = nb / (int32_t) a.ld0, ipn = nb - rr * (int32_t) a.ld0;
+              int32_t rr, ipn;
+              split_subspot(nb, (int32_t) a.ld0, inv_ld0, rr, ipn);
               if (ipn == (int32_t) ip) { more_same_parent = true; continue; }
               deg_more++;
               const int z2 = a.fuse ? (int) __ldcg(a.z + nb) : (int) a.z[nb];
@@ -361,6 +392,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
     if (scalar_sums) tile_cluster_fold<D>(accP, P, q, acc, a.SL, tid);
     __syncthreads();
     double *out = a.partials + (size_t) a.seg_slot[seg] * E;
+#pragma unroll 1
     for (int e2 = tid; e2 < E; e2 += kBlock) out[e2] = acc[e2];
     __syncthreads();
   }

@@ -1,6 +1,7 @@
 // param_kernel.cu -- k_param: the once-per-iteration "small" kernel of every sampler.
 //
-// One CTA of 256 threads.  (0) folds the per-segment statistics of the previous sweep in a fixed two-level
+// One CTA of 512 threads (256 for the run-time-d reference version).  (0) folds the per-segment statistics of the
+// previous sweep in a fixed two-level
 // order (bit-reproducible, independent of grid size and GPU count) and closes plogLik of that sweep;
 // (1) draws mu_k | . for every cluster; (2) draws Lambda | . from the Wishart (Bartlett) and factorises it
 // ONCE for the whole sweep; (3) publishes the parameter block (ParamLayout) the sweep CTAs stage into shared
@@ -106,7 +107,7 @@ __device__ __forceinline__ void blk_inv_upper(int off_U, int off_T, int off_rd, 
 // (the first version, unrolled for DM = 16 with run-time d, was 445 KB of SASS and twice as slow at 10M spots
 // as at 5k spots for that reason alone).
 template <int D>
-__device__ __forceinline__ void warp_revchol_reg(double *U, int lane, int *ok) {
+__device__ __noinline__ void warp_revchol_reg(double *U, int lane, int *ok) {
   double c[D];   // column `lane`, rows 0..lane; entries below the diagonal are never read (don't care)
 #pragma unroll
   for (int i = 0; i < D; i++) c[i] = (lane < D && i <= lane) ? U[lane * D + i] : 0.0;
@@ -132,7 +133,7 @@ __device__ __forceinline__ void warp_revchol_reg(double *U, int lane, int *ok) {
 
 // T = U^-1 (upper), row by row from the bottom; U and T in shared memory (may not alias).
 template <int D>
-__device__ __forceinline__ void warp_inv_upper_reg(const double *U, double *T, int lane) {
+__device__ __noinline__ void warp_inv_upper_reg(const double *U, double *T, int lane) {
   double t[D];   // column `lane` of T; t[k] = 0 for k > lane, so the sums below need no predicate
   if (lane < D) T[lane * D + lane] = 1.0 / U[lane * D + lane];   // reciprocal diagonals, read back as broadcasts
   __syncwarp();
@@ -151,10 +152,10 @@ __device__ __forceinline__ void warp_inv_upper_reg(const double *U, double *T, i
 
 // D = exact dimension 1..32 (register path) or 0 (run-time d up to 32, shared-memory path)
 template <int D>
-__global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, int batch) {
+__global__ void __launch_bounds__(D > 0 ? 512 : 256) k_param(ParamArgs a, int stats_in_smem, int batch) {
   extern __shared__ double sm[];
   __shared__ int s_ok;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   // d stays a run-time value outside the factorisations: compile-time d would fully unroll every small loop below
   // (+120 KB of code that is fetched from HBM once per iteration for nothing)
   const int d = a.PL.d, q = a.PL.q, nl = a.PL.nl, np = a.PL.np, E = a.SL.E;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
 
   // plogLik of the sweep that just finished (uses the parameters of that sweep, still in P: the density matrix and its
   // log-determinant are only replaced in phase (2)).  One warp; when a warp is idle during the factorisations of the mu
-  // phase (q <= 7) it runs there, off the critical path.
+  // phase (fewer clusters than warps) it runs there, off the critical path.
   auto close_plogLik = [&]() {
     double pl;
     if (!a.vvv) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       if (a.ychange) a.ychange[it_prev] = st[a.SL.nacc] / a.n0;   // src/cluster.cpp:1055
     }
   };
-  const bool plog_late = !a.finalize_only && q <= 7 && D > 0;
+  const bool plog_late = !a.finalize_only && q < nw && D > 0;
   if (it_prev >= 1u && warp == 0 && !plog_late) close_plogLik();
   if (a.finalize_only) return;
   if (*a.err) return;
@@ -242,6 +243,41 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
   // ---- (1) mu_k ~ N(var (lambda0 mu0 + Lambda_k s_k), var), var = (lambda0 + n_k Lambda_k)^-1 ---
   // rmvnorm(1, mean, var) = eps chol(var) + mean with chol(var) = R = U^-1, lambda0 + n_k Lambda_k = U U^T,
   // and mean = var rhs = R^T (R rhs):   mu_k = R^T (eps + R rhs).   All clusters of a batch at once.
+  // Bartlett factor A of the Wishart draw (lower triangular: N(0,1) below the diagonal, sqrt(chi2(df - i)) on it).
+  auto bartlett = [&](int kk, int ia, int ib) {
+    double av = 0.0;
+    if (ia > ib) {
+      av = rng_normal(key, P_WISH_NORM, (uint32_t) kk, it, (uint32_t) (ia * (ia - 1) / 2 + ib));
+    } else if (ia == ib) {
+      const int df = (int) ((a.vvv ? st[a.SL.cnt + kk] : (double) a.n) + a.alpha);   // Q4: int df
+      const double chi = rng_gamma(key, P_WISH_CHI, (uint32_t) kk * 1024u + (uint32_t) ia, it, (df - ia) / 2.0, 2.0);
+      if (!(chi > 0.0)) s_ok = 0;                // Q9: df - i <= 0 (empty cluster)
+      av = sqrt(chi);
+    }
+    return av;
+  };
+  // Everything of the iteration that depends on the random numbers and the statistics alone -- the Bartlett factors
+  // (-> MD, idle until phase (2)), the normals of the mean draws (-> vb) and the right-hand sides lambda0 mu0 +
+  // Lambda_k s_k (-> va) -- is side work: when all matrices fit one batch, the warps without a factorisation in phase
+  // (1) do it while the others factorise (4 of 16 warps are busy at q = 4), instead of every thread afterwards.
+  const bool early = D > 0 && batch >= q;
+  auto side_work = [&](int t0, int nthreads) {
+    const int nA = nl * (int) dd, nE = q * d;
+    for (int idx = t0; idx < nA + 2 * nE; idx += nthreads) {
+      if (idx < nA) {
+        const int b = idx / (int) dd, e = idx - b * (int) dd;
+        MD[idx] = bartlett(b, e % d, e / d);
+      } else if (idx < nA + nE) {
+        const int r = idx - nA, k = r / d, i = r - k * d;
+        vb[r] = rng_normal(key, P_MU, (uint32_t) k, it, (uint32_t) i);
+      } else {
+        const int r = idx - nA - nE, k = r / d, i = r - k * d;
+        double s = a.lm0[i];
+        for (int j = 0; j < d; j++) s += MAT(MC, k, i, j) * st[a.SL.sk + k * d + j];
+        va[r] = s;
+      }
+    }
+  };
   for (int k0 = 0; k0 < q; k0 += batch) {
     const int nb = min(batch, q - k0);
     for (int idx = tid; idx < nb * (int) dd; idx += nt) {
@@ -252,27 +288,33 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
     }
     __syncthreads();
     if constexpr (D > 0) {
+      // too few idle warps for the side work to finish before the factorisations: everybody, before them
+      const int busy = min(nb, nw);
+      const bool side_all = early && (nl * (int) dd + 2 * q * d) > 4 * (nt - busy * 32);
+      if (plog_late && k0 == 0 && warp == nw - 1 && it_prev >= 1u) close_plogLik();   // an idle warp of this phase
+      if (early && (side_all || warp >= busy)) side_work(side_all ? tid : tid - busy * 32, side_all ? nt : nt - busy * 32);
 #pragma unroll 1   // one copy of the unrolled factorisations, not four
-      for (int b = warp; b < nb; b += 8) {
+      for (int b = warp; b < nb; b += nw) {
         warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);            // MA = U
         warp_inv_upper_reg<D>(MA + b * dd, MB + b * dd, lane);    // MB = R = chol_upper(var)
       }
-      if (plog_late && k0 == 0 && warp == 7 && it_prev >= 1u) close_plogLik();   // the idle warp of this phase
       __syncthreads();
     } else {
       blk_revchol((int) (MA - sm), nb, d, &s_ok);
       blk_inv_upper((int) (MA - sm), (int) (MB - sm), (int) (va - sm), nb, d);
     }
-    for (int idx = tid; idx < nb * d; idx += nt) {   // va = lambda0 mu0 + Lambda_k s_k
-      const int b = idx / d, i = idx - b * d, k = k0 + b;
-      double s = a.lm0[i];
-      for (int j = 0; j < d; j++) s += MAT(MC, b, i, j) * st[a.SL.sk + k * d + j];
-      va[k * d + i] = s;
+    if (!early) {
+      for (int idx = tid; idx < nb * d; idx += nt) {   // va = lambda0 mu0 + Lambda_k s_k
+        const int b = idx / d, i = idx - b * d, k = k0 + b;
+        double s = a.lm0[i];
+        for (int j = 0; j < d; j++) s += MAT(MC, b, i, j) * st[a.SL.sk + k * d + j];
+        va[k * d + i] = s;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     for (int idx = tid; idx < nb * d; idx += nt) {   // vb = R rhs + eps
       const int b = idx / d, i = idx - b * d, k = k0 + b;
-      double s = rng_normal(key, P_MU, (uint32_t) k, it, (uint32_t) i);
+      double s = early ? vb[k * d + i] : rng_normal(key, P_MU, (uint32_t) k, it, (uint32_t) i);
       for (int j = i; j < d; j++) s += MAT(MB, b, i, j) * va[k * d + j];
       vb[k * d + i] = s;
     }
@@ -306,23 +348,13 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
         }
       }
       MA[idx] = s;
-      // Bartlett factor A (lower triangular): N(0,1) below the diagonal, sqrt(chi2(df - i)) on it
-      double av = 0.0;
-      if (ia > ib) {
-        av = rng_normal(key, P_WISH_NORM, (uint32_t) kk, it, (uint32_t) (ia * (ia - 1) / 2 + ib));
-      } else if (ia == ib) {
-        const int df = (int) ((a.vvv ? st[a.SL.cnt + kk] : (double) a.n) + a.alpha);   // Q4: int df
-        const double chi = rng_gamma(key, P_WISH_CHI, (uint32_t) kk * 1024u + (uint32_t) ia, it, (df - ia) / 2.0, 2.0);
-        if (!(chi > 0.0)) s_ok = 0;                // Q9: df - i <= 0 (empty cluster)
-        av = sqrt(chi);
-      }
-      MC[idx] = av;
+      MC[idx] = early ? MD[idx] : bartlett(kk, ia, ib);   // Bartlett factor A
     }
     __syncthreads();
     BSB_T(6);
     if constexpr (D > 0) {
 #pragma unroll 1   // one copy of the unrolled factorisations, not four
-      for (int b = warp; b < nb; b += 8) {
+      for (int b = warp; b < nb; b += nw) {
         warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);            // V + S = U U^T
         warp_inv_upper_reg<D>(MA + b * dd, MB + b * dd, lane);    // MB = C = chol_upper((V + S)^-1)
       }
@@ -358,13 +390,13 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
     if (q1) {
       if constexpr (D > 0) {
 #pragma unroll 1
-        for (int b = warp; b < nb; b += 8) warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);   // Lambda = rooti rooti^T
+        for (int b = warp; b < nb; b += nw) warp_revchol_reg<D>(MA + b * dd, lane, &s_ok);   // Lambda = rooti rooti^T
         __syncthreads();
       } else {
         blk_revchol((int) (MA - sm), nb, d, &s_ok);
       }
     } else {
-      for (int b = warp; b < nb; b += 8)
+      for (int b = warp; b < nb; b += nw)
         if (lane < d) MAT(MA, b, lane, lane) = MAT(MD, b, lane, lane);
       __syncthreads();
     }
@@ -382,7 +414,7 @@ __global__ void __launch_bounds__(256) k_param(ParamArgs a, int stats_in_smem, i
       MD[idx] = s;
       if (i <= j) P[a.PL.PM + (size_t) kk * np + pair_index(i, j, d)] = (i == j ? 1.0 : 2.0) * s;
     }
-    for (int b = warp; b < nb; b += 8) {           // log-determinant term: sum log diag(rooti)
+    for (int b = warp; b < nb; b += nw) {           // log-determinant term: sum log diag(rooti)
       double ld = lane < d ? log(MAT(MA, b, lane, lane)) : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
@@ -468,7 +500,9 @@ void launch_param(const ParamArgs &a, cudaStream_t stream) {
   // factorisations with one register-resident column per lane, kernel instantiated for the exact d (k_param<0>,
   // the shared-memory version with run-time d, stays as the reference implementation: BSB200_PARAM_GENERIC=1)
   static const bool generic = std::getenv("BSB200_PARAM_GENERIC") != nullptr;
-  param_kernel_table()[generic ? 0 : d]<<<1, 256, smem, stream>>>(a, stats_in_smem, batch);
+  // 16 warps for the register-resident version: one cluster's factorisations per warp up to q = 16 in one round
+  const bool reg = !generic && d > 0;
+  param_kernel_table()[reg ? d : 0]<<<1, reg ? 512 : 256, smem, stream>>>(a, stats_in_smem, batch);
 }
 
 #ifdef BSB_PARAM_TIMING

@@ -3,6 +3,10 @@ import sys, time
 sys.path.insert(0, ".")
 import numpy as np
 import bayesspace_b200 as B
+import os
+if os.environ.get('AB_LIB'):   # A/B of two builds on one box
+    import bayesspace_b200._lib as _L
+    _L.LIB_PATH = os.path.abspath(os.environ['AB_LIB'])
 import bench
 from bayesspace_b200 import synth
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 500

@@ -2,6 +2,9 @@ import sys, ctypes as C; sys.path.insert(0,'.')
 import numpy as np
 import bayesspace_b200 as B, bench
 from bayesspace_b200 import _lib
+import os
+if os.environ.get('AB_LIB'):
+    _lib.LIB_PATH = os.path.abspath(os.environ['AB_LIB'])
 for name in ['c2','c4','c5']:
     w, csr, colour = bench.build_workload(name)
     ch = B.Chain(*bench.chain_args(w, csr, 100000, 100), model=w.model, precision=w.precision, seed=1, colour=colour)
