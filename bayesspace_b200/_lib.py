@@ -67,7 +67,7 @@ EXPORTS = [
     "bsb200_neighbors_lattice", "bsb200_neighbors_radius", "bsb200_parse_neighbor_strings",
     "bsb200_subspot_neighbors", "bsb200_neighbors_to_matrix4", "bsb200_colour_graph", "bsb200_colour_lattice",
     "bsb200_cluster", "bsb200_comm_unique_id", "bsb200_shard_plan", "bsb200_chain_create", "bsb200_chain_run", "bsb200_chain_profile", "bsb200_chain_state",
-    "bsb200_chain_destroy", "bsb200_kernel_launches", "bsb200_eval_loglik", "bsb200_eval_suffstats",
+    "bsb200_chain_destroy", "bsb200_kernel_launches", "bsb200_release_memory", "bsb200_eval_loglik", "bsb200_eval_suffstats",
     "bsb200_chain_dry_sweep", "bsb200_debug_rng", "bsb200_debug_rendezvous", "bsb200_deconv",
     "bsb200_set_snapshot_sink", "bsb200_chain_file_open", "bsb200_chain_file_close", "bsb200_map_subspot2ref", "bsb200_compute_corr", "bsb200_init_cluster",
 ]
@@ -120,3 +120,8 @@ def device_count():
 
 def kernel_launches():
     return int(lib().bsb200_kernel_launches())
+
+
+def release_memory(device=0):
+    """Hand the device and page-locked memory cached from destroyed chains back to the driver."""
+    check(lib().bsb200_release_memory(int(device)))

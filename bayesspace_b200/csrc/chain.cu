@@ -13,11 +13,14 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 
 #include "comm.hpp"
+#include "setup_kernels.hpp"
 #include "shard.hpp"
 #include "tma_maps.hpp"
 
@@ -119,6 +122,26 @@ size_t device_smem_limit() {
   return (size_t) v;
 }
 
+cudaError_t pool_alloc(void **p, size_t bytes) {
+  cudaError_t e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+  if (e == cudaErrorMemoryAllocation) {   // cached blocks of other sizes may be in the way: hand them back and retry
+    cudaGetLastError();
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      cudaDeviceSynchronize();
+      cudaMemPoolTrimTo(pool, 0);
+      e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+    }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);   // valid on every stream from here on
+  return e;
+}
+void pool_free(void *p) {
+  cudaDeviceSynchronize();   // what cudaFree implied: nothing in flight reads the block
+  cudaFreeAsync(p, cudaStreamPerThread);
+}
+
 int select_device(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -130,6 +153,10 @@ int select_device(int device) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(BSB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  cudaMemPool_t pool;   // keep freed blocks mapped (chain.hpp: pool_alloc)
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = ~0ull;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   return BSB200_OK;
 }
 
@@ -157,8 +184,7 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
   });
   for (size_t b = 0; b < nb; b++)
     for (int t = 0; t < nchunk; t++) cnt[b] += ccnt[(size_t) t][b];
-  for (size_t b = 0; b < nb; b++) start[b + 1] = (start[b] + cnt[b] + align - 1) / align * align;
-  npos = nb ? start[nb - 1] + cnt[nb - 1] : 0;
+  layout(cnt, seg_spots, align, start);
   perm.assign((size_t) npos, -1);
   inv.resize((size_t) n_own);
   for (size_t b = 0; b < nb; b++) {   // first position of chunk t inside bucket b
@@ -173,6 +199,17 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
       inv[(size_t) (j - lo)] = (int32_t) pos;
     }
   });
+  return BSB200_OK;
+}
+
+// Positions of the (shard, colour) buckets (aligned starts, holes between them) and the segment / slot tables, from the
+// bucket sizes alone: shared by the host order above and the device order (setup_kernels.cu).  ncol, ngroups set.
+void SpotOrder::layout(const std::vector<int64_t> &cnt, int seg_spots, int align, std::vector<int64_t> &start) {
+  const size_t nb = (size_t) ngroups * ncol;
+  if (align < 1) align = 1;
+  start.assign(nb + 1, 0);
+  for (size_t b = 0; b < nb; b++) start[b + 1] = (start[b] + cnt[b] + align - 1) / align * align;
+  npos = nb ? start[nb - 1] + cnt[nb - 1] : 0;
   seg_begin.clear(); seg_count.clear(); seg_slot.clear();
   colour_seg_start.assign((size_t) ncol + 1, 0);
   group_start.assign((size_t) ngroups + 1, 0);
@@ -199,7 +236,6 @@ int SpotOrder::build(int64_t n, const int32_t *colour, int ncolours, int ngroups
     seg_slot.insert(seg_slot.end(), cs[(size_t) c].begin(), cs[(size_t) c].end());
   }
   colour_seg_start[(size_t) ncol] = (int32_t) seg_begin.size();
-  return BSB200_OK;
 }
 
 int choose_groups(int64_t n) { return n >= 262144 ? kGroups : 1; }
@@ -241,6 +277,30 @@ static int upload(DevBuf<T> &buf, const T *host, size_t count, cudaStream_t s) {
 
 using namespace bsb;
 
+namespace bsb {
+// Page-locked snapshot staging (120 MB at 10M spots) is expensive to lock and unlock: the buffers of the last chain that
+// was destroyed are kept and handed to the next one that fits (one set per process; freed with the CUDA context).
+struct PinnedCache {
+  std::mutex mu;
+  void *z = nullptr, *w = nullptr;
+  size_t count = 0;
+  int device = -1;
+  bool take(int dev, size_t n, int32_t **pz, double **pw) {
+    std::lock_guard<std::mutex> l(mu);
+    if (!z || device != dev || count < n) return false;
+    *pz = (int32_t *) z; *pw = (double *) w;
+    z = w = nullptr; count = 0;
+    return true;
+  }
+  void give(int dev, size_t n, int32_t *pz, double *pw) {
+    std::lock_guard<std::mutex> l(mu);
+    if (z) { cudaFreeHost(z); cudaFreeHost(w); }
+    z = pz; w = pw; count = n; device = dev;
+  }
+};
+static PinnedCache g_pinned;
+}   // namespace bsb
+
 struct bsb200_chain {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -266,6 +326,7 @@ struct bsb200_chain {
   std::vector<double> ybar_host;
   int32_t *h_snap_z = nullptr;   // pinned staging of one snapshot
   double *h_snap_w = nullptr;
+  size_t h_snap_count = 0;       // elements each of them holds
   cudaGraphExec_t graph_iter = nullptr, graph_batch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t iters_done = 0;
@@ -283,15 +344,31 @@ struct bsb200_chain {
   bool have_maps = false;
 
   ~bsb200_chain() {
+    const bool timing = std::getenv("BSB200_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t = now();
+    auto mark = [&](const char *what) {
+      if (!timing) return;
+      const double t2 = now();
+      std::fprintf(stderr, "[bsb200 destroy] %-22s %8.1f ms\n", what, t2 - t);
+      t = t2;
+    };
     if (stream) cudaStreamSynchronize(stream);
+    mark("sync");
     if (graph_iter) cudaGraphExecDestroy(graph_iter);     // graphs first: NCCL waits for the graphs that captured it
     if (graph_batch) cudaGraphExecDestroy(graph_batch);
+    mark("graphs");
     comm.shutdown();               // unmap the peers before the exported label array goes away
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    if (h_snap_z) cudaFreeHost(h_snap_z);
-    if (h_snap_w) cudaFreeHost(h_snap_w);
+    if (h_snap_z && h_snap_w) g_pinned.give(device, h_snap_count, h_snap_z, h_snap_w);
+    else {
+      if (h_snap_z) cudaFreeHost(h_snap_z);
+      if (h_snap_w) cudaFreeHost(h_snap_w);
+    }
+    mark("pinned buffers");
     if (stream) cudaStreamDestroy(stream);
+    Y.release(); ell.release(); mark("Y, ell");
   }
 
   int world() const { return plan.world; }
@@ -519,39 +596,82 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   } pin;
   pin.th = std::thread([&, device = a->device, chp = ch.get()]() {
     pin.e = cudaSetDevice(device);
-    if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_z, sizeof(int32_t) * std::max<int64_t>(n_own, 1));
-    if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_w, sizeof(double) * std::max<int64_t>(n_own, 1));
+    const size_t cnt = (size_t) std::max<int64_t>(n_own, 1);
+    chp->h_snap_count = cnt;
+    if (pin.e == cudaSuccess && g_pinned.take(device, cnt, &chp->h_snap_z, &chp->h_snap_w)) return;
+    if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_z, sizeof(int32_t) * cnt);
+    if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_w, sizeof(double) * cnt);
   });
+  // Unsharded chains order the spots and build the neighbour lists on the device (setup_kernels.cu) from the CSR
+  // arrays, which therefore go first; BSB200_HOST_SETUP=1 keeps the host version (the one sharded chains use).
+  const bool dev_setup = world == 1 && !std::getenv("BSB200_HOST_SETUP");
+  DeviceOrder dorder;
+  std::promise<int> csr_promise;
+  std::future<int> csr_ready = csr_promise.get_future();
   yup.th = std::thread([&, device = a->device]() {
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&Yraw.p, sizeof(double) * std::max<size_t>((size_t) n_own * d, 1));
+    if (dev_setup) {
+      int rcu = e == cudaSuccess ? dorder.upload(a->nbr_ptr, a->nbr_idx, a->init, a->colour, n, device) : BSB200_ERR_CUDA;
+      if (rcu) yup.msg = g_last_error;   // thread-local message of this thread
+      csr_promise.set_value(rcu);
+      if (rcu) { yup.rc = rcu; return; }
+    }
+    if (e == cudaSuccess && Yraw.alloc((size_t) n_own * d)) { yup.rc = BSB200_ERR_CUDA; yup.msg = g_last_error; return; }
     if (e == cudaSuccess) {
-      Yraw.count = (size_t) n_own * d;
-      e = cudaMemcpy2D(Yraw.p, sizeof(double) * n_own, a->Y + plan.lo, sizeof(double) * n, sizeof(double) * n_own, (size_t) d,
-                       cudaMemcpyHostToDevice);
+      std::vector<StagedCopy> cols;   // own rows of every column of R's column-major n x d matrix
+      if (n_own == n) cols.push_back({Yraw.p, a->Y, sizeof(double) * (size_t) n * d});
+      else
+        for (int c = 0; c < d; c++) cols.push_back({Yraw.p + (size_t) c * n_own, a->Y + (size_t) c * n + plan.lo, sizeof(double) * (size_t) n_own});
+      const int rcu = staged_h2d(device, cols.data(), (int) cols.size());
+      if (rcu) { yup.rc = rcu; yup.msg = g_last_error; }
     }
     if (e != cudaSuccess) { yup.rc = BSB200_ERR_CUDA; yup.msg = cudaGetErrorString(e); }
+    if (timing) std::fprintf(stderr, "[bsb200 setup] Y upload thread done at %8.1f ms\n", now_ms() - t0);
   });
 
   // ---- colouring (of the whole graph: every rank derives the same classes) ------------------------
   std::vector<int32_t> colour;
   int32_t ncol = 0;
-  if (a->colour) {
-    if (a->ncolours < 1 || a->ncolours > 64) return fail(BSB200_ERR_INVALID, "ncolours = %d out of range", a->ncolours);
-    colour.assign(a->colour, a->colour + n);
-    ncol = a->ncolours;
-    for (int64_t j = 0; j < n; j++)
-      if (colour[(size_t) j] < 0 || colour[(size_t) j] >= ncol) return fail(BSB200_ERR_INVALID, "colour[%lld] out of range", (long long) j);
-    if (!colouring_is_proper(a->nbr_ptr, a->nbr_idx, n, colour.data())) {
-      colour.clear();   // e.g. hex offsets on a filled rectangle: colour the graph ourselves
+  std::vector<int64_t> bucket_cnt, bucket_start;
+  int dev_maxdeg = 0;
+  if (a->colour && (a->ncolours < 1 || a->ncolours > 64)) return fail(BSB200_ERR_INVALID, "ncolours = %d out of range", a->ncolours);
+  if (dev_setup) {
+    CK(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
+    if ((rc = dorder.prealloc(n))) { csr_ready.wait(); return rc; }
+    if ((rc = csr_ready.get())) return fail(rc, "%s", yup.msg.c_str());
+    mark("graph upload");
+    bool proper = false;
+    if (a->colour) {   // range and properness are checked by the scan
+      ncol = a->ncolours;
+      if ((rc = dorder.scan(nullptr, ncol, G, ch->stream, bucket_cnt, &dev_maxdeg, &proper))) return rc;
     }
+    if (!proper) {   // none given, or e.g. hex offsets on a filled rectangle: colour the graph ourselves
+      rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
+      if (rc) return rc;
+      if ((rc = dorder.scan(colour.data(), ncol, G, ch->stream, bucket_cnt, &dev_maxdeg, &proper))) return rc;
+      if (!proper) return fail(BSB200_ERR_NEIGHBORS, "internal error: greedy colouring is not proper");
+    }
+    mark("colouring");
+    ch->ord.ncol = ncol;
+    ch->ord.ngroups = G;
+    ch->ord.layout(bucket_cnt, choose_segment(n, ncol, d), kOrderAlign, bucket_start);
+  } else {
+    if (a->colour) {
+      colour.assign(a->colour, a->colour + n);
+      ncol = a->ncolours;
+      for (int64_t j = 0; j < n; j++)
+        if (colour[(size_t) j] < 0 || colour[(size_t) j] >= ncol) return fail(BSB200_ERR_INVALID, "colour[%lld] out of range", (long long) j);
+      if (!colouring_is_proper(a->nbr_ptr, a->nbr_idx, n, colour.data())) {
+        colour.clear();   // e.g. hex offsets on a filled rectangle: colour the graph ourselves
+      }
+    }
+    if (colour.empty()) {
+      rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
+      if (rc) return rc;
+    }
+    mark("colouring");
+    ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol, d), plan.g0, plan.g1, plan.lo, plan.hi, kOrderAlign);
   }
-  if (colour.empty()) {
-    rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
-    if (rc) return rc;
-  }
-  mark("colouring");
-  ch->ord.build(n, colour.data(), ncol, G, choose_segment(n, ncol, d), plan.g0, plan.g1, plan.lo, plan.hi, kOrderAlign);
   const SpotOrder &ord = ch->ord;
   const int64_t n_pos = ch->n_pos = ord.npos;   // ghosts follow the own positions
   ch->ld = (n_pos + (int64_t) plan.ghosts.size() + 31) / 32 * 32;
@@ -602,7 +722,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   }
 
   // ---- device staging --------------------------------------------------------------------------
-  CK(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
+  if (!ch->stream) CK(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
   cudaStream_t s = ch->stream;
   CK(cudaEventCreate(&ch->ev0));
   CK(cudaEventCreate(&ch->ev1));
@@ -615,8 +735,8 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     ch->z.adopt(ch->comm.z(), (size_t) ch->ld);
     ch->recv_pos.adopt(ch->comm.recv_pos(), ch->halo.recv_pos.size());
   }
-  int maxdeg = 0;
-  {
+  int maxdeg = dev_maxdeg;
+  if (!dev_setup) {
     std::vector<int> md((size_t) parallel_chunks(n), 0);
     parallel_for(n, [&](int64_t lo, int64_t hi, int t) {
       int m = 0;
@@ -626,7 +746,14 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     for (int m : md) maxdeg = std::max(maxdeg, m);
   }
   ch->maxdeg = maxdeg;
-  {
+  if (dev_setup) {
+    // original ids, initial labels and neighbour lists in internal order, written by the device from the uploaded graph
+    const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;
+    if ((rc = ch->ell.alloc(ell_rows * ldp + kSweepPad)) || (rc = ch->z.alloc(ldp + kSweepPad)) ||
+        (rc = ch->orig.alloc(ldp + kSweepPad)))
+      return rc;
+    if ((rc = dorder.place(bucket_cnt, bucket_start, ch->ld, maxdeg, ch->orig.p, ch->z.p, ch->ell.p, s))) return rc;
+  } else {
     // neighbour ids in internal order (ELL, -1 padded), initial labels and original ids, filled by host threads
     const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;
     std::unique_ptr<int32_t[]> ell(new int32_t[ell_rows * ldp + kSweepPad]);
@@ -840,8 +967,11 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
   auto flush_pending = [&]() {
     if (pending_row < 0) return;
     const size_t r = (size_t) pending_row;
-    if (out->z) std::memcpy(out->z + r * ch->n + ch->lo, ch->h_snap_z, sizeof(int32_t) * ch->n_own);
-    if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n + ch->lo, ch->h_snap_w, sizeof(double) * ch->n_own);
+    // host threads: the destination is fresh pages of the caller's matrices (page faults, not bandwidth)
+    parallel_for(ch->n_own, [&](int64_t a, int64_t b, int) {
+      if (out->z) std::memcpy(out->z + r * ch->n + ch->lo + a, ch->h_snap_z + a, sizeof(int32_t) * (size_t) (b - a));
+      if (out->weights && ch->tdist) std::memcpy(out->weights + r * ch->n + ch->lo + a, ch->h_snap_w + a, sizeof(double) * (size_t) (b - a));
+    });
     if (sink_active() && ch->world() == 1) {   // chain persistence: the row goes to the sink as it is produced
       const int64_t dims[1] = {ch->n};
       int rc = sink_write("z", (int64_t) r, ch->h_snap_z, ch->n, 0, dims, 1);
@@ -943,6 +1073,19 @@ int bsb200_device_count(void) {
 }
 
 int64_t bsb200_kernel_launches(void) { return (int64_t) g_launches.load(); }
+
+int bsb200_release_memory(int32_t device) {
+  int rc = select_device(device);
+  if (rc) return rc;
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemPoolTrimTo(pool, 0));
+  int32_t *z = nullptr;
+  double *w = nullptr;
+  if (g_pinned.take(device, 0, &z, &w)) { cudaFreeHost(z); cudaFreeHost(w); }
+  return BSB200_OK;
+}
 
 int bsb200_chain_create(const bsb200_cluster_args *args, bsb200_chain **chain) {
   if (!chain) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
@@ -1075,9 +1218,22 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   if (!args || !out) return fail(BSB200_ERR_INVALID, "Invalid arguments!");
   g_cancel.store(0);
   bsb200_chain *ch = nullptr;
+  static const bool timing = std::getenv("BSB200_TIMING") != nullptr;
+  double t_last = now_ms();
+  auto mark = [&](const char *what) {   // BSB200_TIMING=1: wall-clock marks on stderr
+    if (!timing) return;
+    const double t = now_ms();
+    std::fprintf(stderr, "[bsb200 cluster] %-24s %8.1f ms\n", what, t - t_last);
+    t_last = t;
+  };
   int rc = chain_create_impl(args, &ch);
   if (rc) return rc;
-  std::unique_ptr<bsb200_chain> guard(ch);
+  mark("chain create");
+  struct Guard {   // destroys the chain, timed
+    bsb200_chain *ch;
+    decltype(mark) &mk;
+    ~Guard() { delete ch; mk("chain destroy"); }
+  } guard{ch, mark};
   const int64_t n = args->n;
   const int d = args->d, q = args->q, nsnap = args->nrep / args->thin + 1, nl = ch->nl;
   // row 0 of every output = initial state (src/cluster.cpp:232-237, 462-469); rows the chain does not reach stay
@@ -1085,14 +1241,13 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   // of an interrupted run are zeroed (at the end) -- a second pass over 1.3 GB of host memory at 10M spots otherwise.
   // Sharded: a rank writes its own columns only, the others are zeroed up front.
   const bool sharded = ch->world() > 1;
-  if (out->z) {
-    if (sharded) std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
-    std::memcpy(out->z, args->init, sizeof(int32_t) * n);
-  }
-  if (out->weights && ch->tdist) {
-    if (sharded) std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
-    for (int64_t j = 0; j < n; j++) out->weights[j] = 1.0;
-  }
+  if (out->z && sharded) std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
+  if (out->weights && ch->tdist && sharded) std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
+  parallel_for(n, [&](int64_t a, int64_t b, int) {
+    if (out->z) std::memcpy(out->z + a, args->init + a, sizeof(int32_t) * (size_t) (b - a));
+    if (out->weights && ch->tdist)
+      for (int64_t j = a; j < b; j++) out->weights[j] = 1.0;
+  });
   if (!sharded && args->thin == 1 && nsnap > 1) {
     // iteration i is stored in row (i + 1) / thin: with thin = 1 the first iteration lands in row 2 and row 1 is never
     // produced (it stays zero in the reference, src/cluster.cpp:310-313) -- do not leave the caller's bytes there
@@ -1112,9 +1267,11 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   out->setup_ms = ch->setup_ms;
   out->own_lo = ch->lo;
   out->own_hi = ch->hi;
+  mark("row 0");
   double ms = 0.0;
   rc = chain_run_impl(ch, args->nrep - 1, out, &ms, true);
   out->device_ms = ms;
+  mark("chain run (wall)");
   if (!sharded && out->rows_done < nsnap) {   // interrupted (or failed) run: the rows never reached read as zero
     const size_t r0 = (size_t) out->rows_done, nr = (size_t) (nsnap - out->rows_done);
     if (out->z) std::memset(out->z + r0 * n, 0, sizeof(int32_t) * nr * n);
@@ -1123,6 +1280,7 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   if (rc && rc != BSB200_ERR_CANCELLED) return rc;
   int rc2 = chain_finish_impl(ch, out);
   if (rc2) return rc2;
+  mark("finish");
   if (out->mu)
     for (int k = 0; k < q; k++)
       for (int c = 0; c < d; c++) out->mu[k * d + c] = args->mu0[c];

@@ -10,6 +10,13 @@
 namespace bsb {
 
 // Owning device buffer.
+// Device memory comes from the device's default stream-ordered pool with its release threshold raised (chain.cu:
+// select_device), so that a destroyed chain's buffers stay mapped for the next one: cudaFree / cudaMalloc of the 3 GB a
+// 10M-spot chain holds cost between 5 and 600 ms of wall clock per bsb200_cluster() call.  bsb200_release_memory() hands
+// the cached memory back to the driver.  pool_alloc returns memory valid on every stream; pool_free waits for the device.
+cudaError_t pool_alloc(void **p, size_t bytes);
+void pool_free(void *p);
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -18,19 +25,23 @@ struct DevBuf {
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  ~DevBuf() { if (p && owned) cudaFree(p); }
+  ~DevBuf() { if (p && owned) pool_free(p); }
   // a region of somebody else's allocation (the exported arena of the peer transport)
   void adopt(T *ptr, size_t n) {
-    if (p && owned) cudaFree(p);
+    if (p && owned) pool_free(p);
     p = ptr; count = n; owned = false;
   }
+  void release() {
+    if (p && owned) pool_free(p);
+    p = nullptr; count = 0;
+  }
   int alloc(size_t n) {
-    if (p && owned) cudaFree(p);
+    if (p && owned) pool_free(p);
     p = nullptr; owned = true;
     count = n;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e != cudaSuccess) return fail(BSB200_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    cudaError_t e = pool_alloc((void **) &p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(BSB200_ERR_CUDA, "device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
     return BSB200_OK;
   }
 };
@@ -46,6 +57,7 @@ struct SpotOrder {
   std::vector<int32_t> group_start;                      // ngroups + 1 offsets into the slots
   // spots [lo, hi) = virtual shards [g0, g1) of ngroups_total; defaults: everything
   // align: first position of every (shard, colour) range (TMA boxes of k_sweep_fast start at 16-byte boundaries)
+  void layout(const std::vector<int64_t> &cnt, int seg_spots, int align, std::vector<int64_t> &start);
   int build(int64_t n, const int32_t *colour, int ncolours, int ngroups_total, int seg_spots, int g0 = 0, int g1 = -1,
             int64_t lo = 0, int64_t hi = 0, int align = 1);
 };

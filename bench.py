@@ -566,7 +566,7 @@ def run_gpu(args):
     line["e2e"] = {"value": total_units * e2e_iters / e2e_s, "unit": "spot-updates/s",
                    "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
                    "call": "bsb200_cluster(nrep=%d, thin=100) with host buffers: wall clock of the whole call "
-                           "(host-side graph colouring/ordering, H2D, %d sweeps, %d snapshots D2H)" %
+                           "(validation, staged H2D of pageable inputs, spot order and neighbour lists on the device, %d sweeps, %d snapshots D2H)" %
                            (e2e_iters + 1, e2e_iters, nsnap),
                    "wall_s": e2e_s, "setup_ms": out["_info"]["setup_ms"], "device_ms": out["_info"]["device_ms"]}
     # ---- CPU baseline beside it (rank 0, bounded sample) ----------------------------------------------------

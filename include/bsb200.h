@@ -216,6 +216,10 @@ int bsb200_chain_state(bsb200_chain *chain, int32_t *z, double *weights, double 
 int bsb200_chain_destroy(bsb200_chain *chain);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t bsb200_kernel_launches(void);
+/* Device memory of destroyed chains stays in the device's stream-ordered pool for the next chain (allocation and
+ * release of the ~3 GB a 10M-spot chain holds otherwise cost up to hundreds of milliseconds per call), as do the
+ * page-locked snapshot buffers.  This hands both back to the driver; nothing else in the library depends on it. */
+int bsb200_release_memory(int32_t device);
 
 /* ------------------------------------------------------------------------------------------------
  * State-level parity probes (evaluate one quantity of the sampler on a caller-supplied state).
