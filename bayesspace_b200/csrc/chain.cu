@@ -329,6 +329,8 @@ struct bsb200_chain {
   size_t h_snap_count = 0;       // elements each of them holds
   cudaGraphExec_t graph_iter = nullptr, graph_batch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;                    // snapshots leave the device beside the next batch of sweeps
+  cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;    // snapshot written (main stream) / on the host (copy stream)
   int64_t iters_done = 0;
   int kernels_per_iter = 0;
   double setup_ms = 0;
@@ -361,6 +363,9 @@ struct bsb200_chain {
     comm.shutdown();               // unmap the peers before the exported label array goes away
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev_snap) cudaEventDestroy(ev_snap);
+    if (ev_copied) cudaEventDestroy(ev_copied);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (h_snap_z && h_snap_w) g_pinned.give(device, h_snap_count, h_snap_z, h_snap_w);
     else {
       if (h_snap_z) cudaFreeHost(h_snap_z);
@@ -726,6 +731,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   cudaStream_t s = ch->stream;
   CK(cudaEventCreate(&ch->ev0));
   CK(cudaEventCreate(&ch->ev1));
+  CK(cudaStreamCreateWithFlags(&ch->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ch->ev_snap, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ch->ev_copied, cudaEventDisableTiming));
   const int nlT = (ch->tdist || ch->vvv) ? ch->nl : 0;
   const StatLayout SL_run = make_stat_layout(q, d, nlT);
   const StatLayout SL_init = make_stat_layout(q, d, 1);   // one-off pass that also yields sum y y^T
@@ -964,8 +972,10 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
   // (the copy touches fresh pages of a 1.3 GB allocation at 10M spots: ~30 ms per row that used to idle the GPU).
   int64_t pending_row = -1;
   int sink_rc = BSB200_OK;
+  bool copy_in_flight = false;
   auto flush_pending = [&]() {
     if (pending_row < 0) return;
+    if (copy_in_flight) { cudaEventSynchronize(ch->ev_copied); copy_in_flight = false; }
     const size_t r = (size_t) pending_row;
     // host threads: the destination is fresh pages of the caller's matrices (page faults, not bandwidth)
     parallel_for(ch->n_own, [&](int64_t a, int64_t b, int) {
@@ -1001,6 +1011,8 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
       const int64_t row = (ch->iters_done + 1) / ch->thin;
       const bool sink = sink_active() && out && ch->world() == 1;
       const bool want_w = ch->tdist && (!out || out->weights || sink);
+      // the previous snapshot must have left snap_z / snap_w (flush_pending above waited for it when a caller takes rows)
+      if (copy_in_flight) CK(cudaStreamWaitEvent(s, ch->ev_copied, 0));
       launch_snapshot(ch->z.p, want_w ? ch->w.p : nullptr, ch->orig.p, ch->n_pos, ch->snap_z.p,
                       want_w ? ch->snap_w.p : nullptr, s, ch->lo);
       if (out && out->z_mode && row >= out->mode_from && row < ch->nrep / ch->thin + 1) {
@@ -1013,8 +1025,13 @@ int chain_run_impl(bsb200_chain *ch, int iters, bsb200_cluster_out *out, double 
         launch_mode_accumulate(ch->snap_z.p, ch->n_own, ch->q, (uint32_t) row, ch->mode_cnt.p, ch->mode_first.p, s);
       }
       // the snapshots travel to the host only when the caller asked for the matrices
-      if (!out || out->z || sink) CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, s));
-      if (want_w) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, s));
+      // ... on the copy stream, so that the next batch of sweeps does not wait for 120 MB over PCIe
+      CK(cudaEventRecord(ch->ev_snap, s));
+      CK(cudaStreamWaitEvent(ch->copy_stream, ch->ev_snap, 0));
+      if (!out || out->z || sink) CK(cudaMemcpyAsync(ch->h_snap_z, ch->snap_z.p, sizeof(int32_t) * ch->n_own, cudaMemcpyDeviceToHost, ch->copy_stream));
+      if (want_w) CK(cudaMemcpyAsync(ch->h_snap_w, ch->snap_w.p, sizeof(double) * ch->n_own, cudaMemcpyDeviceToHost, ch->copy_stream));
+      CK(cudaEventRecord(ch->ev_copied, ch->copy_stream));
+      copy_in_flight = true;
     }
     CK(cudaEventRecord(ch->ev1, s));
     CK(cudaStreamSynchronize(s));

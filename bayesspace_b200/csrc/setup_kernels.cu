@@ -9,6 +9,7 @@
 #include "setup_kernels.hpp"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -31,7 +32,7 @@ static inline void count_launch() { g_launches++; }
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr size_t kStageChunk = 4u << 20;   // bytes per page-locked buffer
-constexpr int kStageWorkers = 6, kStageDepth = 2;
+constexpr int kStageWorkers = 12, kStageDepth = 2;   // buffers exist for 12 workers; stage_workers() of them run
 
 struct StagePool {   // one per process and device, allocated on first use, never freed (like the CUDA context)
   std::mutex mu;
@@ -104,7 +105,12 @@ int staged_h2d(int device, const StagedCopy *copies, int ncopies) {
     if (ew == cudaSuccess) ew = cudaStreamSynchronize(g_pool.stream[w]);
     if (ew != cudaSuccess) err.store((int) ew);
   };
-  const int nw = (int) std::min<size_t>((size_t) kStageWorkers, std::max<size_t>(chunks.size(), 1));
+  static const int want = []() {
+    int v = 6;
+    if (const char *e = std::getenv("BSB200_STAGE_WORKERS")) v = std::atoi(e);
+    return v < 1 ? 1 : (v > kStageWorkers ? kStageWorkers : v);
+  }();
+  const int nw = (int) std::min<size_t>((size_t) want, std::max<size_t>(chunks.size(), 1));
   std::vector<std::thread> th;
   for (int w = 1; w < nw; w++) th.emplace_back(worker, w);
   worker(0);
