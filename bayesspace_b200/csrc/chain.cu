@@ -1256,10 +1256,8 @@ int bsb200_cluster(const bsb200_cluster_args *args, bsb200_cluster_out *out) {
   // row 0 of every output = initial state (src/cluster.cpp:232-237, 462-469); rows the chain does not reach stay
   // zero as in the reference.  Single GPU: every later row is overwritten in full by its snapshot, so only the rows
   // of an interrupted run are zeroed (at the end) -- a second pass over 1.3 GB of host memory at 10M spots otherwise.
-  // Sharded: a rank writes its own columns only, the others are zeroed up front.
+  // Sharded: a rank writes its own columns [own_lo, own_hi) of rows 1.. and nothing else beyond row 0 (include/bsb200.h).
   const bool sharded = ch->world() > 1;
-  if (out->z && sharded) std::memset(out->z, 0, sizeof(int32_t) * (size_t) nsnap * n);
-  if (out->weights && ch->tdist && sharded) std::memset(out->weights, 0, sizeof(double) * (size_t) nsnap * n);
   parallel_for(n, [&](int64_t a, int64_t b, int) {
     if (out->z) std::memcpy(out->z + a, args->init + a, sizeof(int32_t) * (size_t) (b - a));
     if (out->weights && ch->tdist)

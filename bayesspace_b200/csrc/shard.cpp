@@ -42,12 +42,21 @@ int make_halo_plan(const ShardPlan &plan, const int64_t *ptr, const int32_t *idx
     recv[(size_t) colour[u] * W + plan.owner(u)].push_back((int32_t) (ghost_base + (int64_t) gi));
   }
   // what I send: own spots read by a spot of another rank
+  // (every spot of the other ranks is looked at: the lists need not be symmetric; chunks on host threads)
   std::vector<std::vector<int32_t>> need((size_t) W);
-  for (int64_t v = 0; v < plan.n; v++) {
-    if (v >= plan.lo && v < plan.hi) { v = plan.hi - 1; continue; }
-    const int p = plan.owner(v);
-    for (int64_t e = ptr[v]; e < ptr[v + 1]; e++)
-      if (idx[e] >= plan.lo && idx[e] < plan.hi) need[(size_t) p].push_back(idx[e]);
+  {
+    const int nchunk = parallel_chunks(plan.n);
+    std::vector<std::vector<std::vector<int32_t>>> part((size_t) nchunk, std::vector<std::vector<int32_t>>((size_t) W));
+    parallel_for(plan.n, [&](int64_t a, int64_t b, int t) {
+      for (int64_t v = a; v < b; v++) {
+        if (v >= plan.lo && v < plan.hi) { v = plan.hi - 1; continue; }
+        const int p = plan.owner(v);
+        for (int64_t e = ptr[v]; e < ptr[v + 1]; e++)
+          if (idx[e] >= plan.lo && idx[e] < plan.hi) part[(size_t) t][(size_t) p].push_back(idx[e]);
+      }
+    });
+    for (int t = 0; t < nchunk; t++)
+      for (int p = 0; p < W; p++) need[(size_t) p].insert(need[(size_t) p].end(), part[(size_t) t][(size_t) p].begin(), part[(size_t) t][(size_t) p].end());
   }
   for (int p = 0; p < W; p++) {
     auto &v = need[(size_t) p];

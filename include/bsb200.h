@@ -170,7 +170,9 @@ typedef struct bsb200_cluster_out {
   double setup_ms;   /* out: host->device staging + graph setup, wall clock             */
   double device_ms;  /* out: device time of the sampling loop (CUDA events)             */
   int64_t own_lo, own_hi; /* out: spots [own_lo, own_hi) of z / weights were written by this rank
-                             (all of them when world <= 1); mu / lambda / plogLik are complete on every rank */
+                             (all of them when world <= 1); mu / lambda / plogLik are complete on every rank.
+                             A rank of a sharded chain writes row 0 and its own columns of the later rows and leaves
+                             the other ranks' columns as the caller passed them (no pass over the full matrices) */
   /* Optional device-side post-sampling reduction: the per-spot MODE of the label snapshots of rows
    * r >= mode_from, with R's Mode() tie rule (R/utils.R:63-66: among equally frequent labels the one that appears
    * first in the kept rows) -- what spatialCluster() computes with apply(zs, 2, Mode) (R/spatialCluster.R:204-213,

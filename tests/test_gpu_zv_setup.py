@@ -97,3 +97,22 @@ def test_device_setup_general_graph(bsb):
     run = lambda: bsb.cluster(Y, q, (ptr, idx), init=init, model="normal", precision="equal", mu0=Y.mean(axis=0),
                               lambda0=0.01 * np.eye(d), gamma=2.0, alpha=1.0, beta=0.01, nrep=5, thin=1, seed=2)
     _same(*_both(bsb, run))
+
+
+def test_release_memory_and_reuse(bsb):
+    """Device memory of a destroyed chain stays in the pool for the next one; bsb200_release_memory() hands it back and
+    the library keeps working (the next chain allocates afresh)."""
+    import ctypes as C
+    w = _workload("ST", 64, 64, 6, 4, seed=2)
+    _, csr = bsb.neighbors._find_neighbors(w.array_row, w.array_col, w.platform)
+    colour = bsb.colour_lattice(w.array_row, w.array_col, w.platform)
+    run = lambda: bsb.cluster(w.Y, w.q, csr, init=w.init, model="t", precision="equal", mu0=w.mu0, lambda0=w.lambda0,
+                              gamma=w.gamma, alpha=w.alpha, beta=w.beta, nrep=5, thin=1, seed=3, colour=colour)
+    first = run()
+    second = run()          # served from the pool
+    bsb.release_memory(0)
+    third = run()
+    _same(first, second)
+    _same(first, third)
+    with pytest.raises(bsb.BayesSpaceError):
+        bsb.release_memory(99)
