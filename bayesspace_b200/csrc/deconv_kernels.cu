@@ -25,7 +25,7 @@ namespace bsb {
 namespace {
 
 struct DeconvSmem {
-  int gL, cL, PL, tile, sws, wvs, acc, accP, ct, red, zs_bytes_off, P;
+  int gL, cL, PL, tile, sws, wvs, acc, accP, ct, red, logtab, zs_bytes_off, P;
   size_t bytes;
 };
 __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, int E) {
@@ -44,6 +44,8 @@ __host__ __device__ inline DeconvSmem deconv_smem_layout(int D, int q, int np, i
   s.P = q > 16 ? cluster_sum_parts(D, q) : 0;
   s.accP = o; o += s.P * q * (D + 2);
   s.red = o; o += 3 * (kBlock / 32);
+  o = (o + 1) & ~1;
+  s.logtab = o; o += 256;   // 128 (log, reciprocal) pairs of the table logarithm (rng.cuh)
   s.zs_bytes_off = o * 8;
   s.bytes = (size_t) o * 8 + kBlock;
   return s;
@@ -68,12 +70,14 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
   double *s_gL = sm + L.gL, *s_cL = sm + L.cL, *s_PL = sm + L.PL, *tile = sm + L.tile, *sws = sm + L.sws;
   double *wvs = sm + L.wvs, *acc = sm + L.acc, *accP = sm + L.accP, *ct = sm + L.ct, *red = sm + L.red;
   uint8_t *zs = reinterpret_cast<uint8_t *>(sm) + L.zs_bytes_off;
+  double2 *s_logtab = reinterpret_cast<double2 *>(sm + L.logtab);
   const int P = L.P;
   if (*a.err) return;
   const bool scalar_sums = q > 16;
   const int nh = scalar_sums ? 0 : (q + 7) / 8;
   for (int e = tid; e < (DP - D - 1) * kTileLd; e += kBlock) tile[(D + 1) * kTileLd + e] = 0.0;   // padding rows
   if (!a.stats_only) {
+    for (int e = tid; e < 128; e += kBlock) log_table_entry(e, s_logtab[e]);
     const double *P = a.params;
 #pragma unroll 1
     for (int e = tid; e < q * D; e += kBlock) s_gL[e] = P[a.PL.gL + e];
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
 #pragma unroll 1
           for (int c2 = 0; c2 < (D + 1) / 2; c2++) {
             double n0v, n1v;
-            rng_normal2(key, P_ERR, sorig, it, (uint32_t) c2, n0v, n1v);
+            rng_normal2_tab(key, P_ERR, sorig, it, (uint32_t) c2, s_logtab, n0v, n1v);
             tile[(2 * c2) * kTileLd + tid] = a.err_sd * n0v;
             tile[(2 * c2 + 1) * kTileLd + tid] = a.err_sd * n1v;
           }
