@@ -285,6 +285,27 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
         // Neighbours in OTHER parents belong to another colour class and do not change during this launch: their
         // labels are gathered once, before the turns.  Neighbours inside the parent sit on adjacent lanes: their live
         // label is the lane's register, fetched by shuffle at every turn -- no memory traffic inside the scan.
+        // Everything of the scan that does not read a label happens BEFORE the wait for the previous colour class (one
+        // launch for all classes): the neighbour ids, which of them sit in the own parent, and the Potts scale.
+        constexpr int kNbReg = 8;
+        int32_t nbv[kNbReg];
+        int src[kNbReg];
+        int deg = 0;
+#pragma unroll
+        for (int ee = 0; ee < kNbReg; ee++) {
+          nbv[ee] = -1;
+          src[ee] = lane;
+          if (active && ee < a.maxdeg) {
+            const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
+            if (nb >= 0) {
+              deg++;
+              int32_t rr, ipn;
+              split_subspot(nb, (int32_t) a.ld0, inv_ld0, rr, ipn);
+              if (ipn == (int32_t) ip) src[ee] = glane0 + rr;   // same parent: live label of that lane
+              else nbv[ee] = nb;                                  // another parent: gathered after the wait
+            }
+          }
+        }
         if (a.fuse && my_colour > 0) {   // labels of the previous colour classes must be final and visible
           if (tid == 0) {
             const uint32_t target = it * (uint32_t) (a.colour_seg_start[my_colour] - a.colour_seg_start[my_colour - 1]);
@@ -300,24 +321,10 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
           }
           __syncthreads();
         }
-        constexpr int kNbReg = 8;
-        int zu[kNbReg], src[kNbReg];
-        int deg = 0;
+        int zu[kNbReg];
 #pragma unroll
-        for (int ee = 0; ee < kNbReg; ee++) {
-          zu[ee] = -1;
-          src[ee] = lane;
-          if (active && ee < a.maxdeg) {
-            const int32_t nb = a.ell[((size_t) ee * S + r) * a.ld0 + ip];
-            if (nb >= 0) {
-              deg++;
-              int32_t rr, ipn;
-              split_subspot(nb, (int32_t) a.ld0, inv_ld0, rr, ipn);
-              if (ipn == (int32_t) ip) src[ee] = glane0 + rr;   // same parent: live label of that lane
-              else zu[ee] = a.fuse ? (int) __ldcg(a.z + nb) : (int) a.z[nb];
-            }
-          }
-        }
+        for (int ee = 0; ee < kNbReg; ee++)
+          zu[ee] = nbv[ee] >= 0 ? (a.fuse ? (int) __ldcg(a.z + nbv[ee]) : (int) a.z[nbv[ee]]) : -1;
         int deg_more = 0, cp_more = 0, cn_more = 0;   // neighbours beyond kNbReg (general graphs): other parents only counted here
         bool more_same_parent = false;
         if (active)
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
               cn_more += z2 == zn;
             }
           }
-        double pscale = 0.0;
+        double pscale = (deg + deg_more) ? a.gamma / (deg + deg_more) * 2 : 0.0;
         for (int turn = 0; turn < S; turn++) {
           int cp = cp_more, cn = cn_more, dg = deg + deg_more;
 #pragma unroll
@@ -356,13 +363,15 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
               }
             double pot_p = 0.0, pot_n = 0.0;
             if (dg) {
-              pscale = a.gamma / dg * 2;
+              if (more_same_parent) pscale = a.gamma / dg * 2;
               pot_p = pscale * cp;
               pot_n = pscale * cn;
             }
-            const double prob = exp((pot_n - pot_p) + dl_z);
-            if (prob != prob) atomicExch(a.err, BSB_DEVERR_NUMERIC);
-            const bool upd = prob >= 1.0 ? true : sample_two(prob, u_acc_z);
+            // accept with probability min(1, exp(delta)) (:1043-1046), decided in the log domain like the cluster samplers'
+            // sweep (rng.cuh: mh_accept): no exponential inside the turns unless the decision is within its rounding
+            const double delta = (pot_n - pot_p) + dl_z;
+            if (delta != delta) atomicExch(a.err, BSB_DEVERR_NUMERIC);
+            const bool upd = mh_accept(delta, u_acc_z);
             if (upd) {
               a.z[si] = (uint8_t) zn;
               zfinal = zn;
