@@ -306,6 +306,20 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
             }
           }
         }
+        // lanes of the own parent this subspot reads at every turn, compacted to the front (static indices only); the
+        // turns shuffle nsp_max labels instead of kNbReg
+        int sps[kNbReg], nsp = 0;
+#pragma unroll
+        for (int ee = 0; ee < kNbReg; ee++) sps[ee] = lane;
+#pragma unroll
+        for (int ee = 0; ee < kNbReg; ee++) {
+          const bool same = src[ee] != lane;
+#pragma unroll
+          for (int k = 0; k < kNbReg; k++)
+            if (same && k == nsp) sps[k] = src[ee];
+          nsp += same;
+        }
+        const int nsp_max = __reduce_max_sync(0xffffffffu, nsp);
         if (a.fuse && my_colour > 0) {   // labels of the previous colour classes must be final and visible
           if (tid == 0) {
             const uint32_t target = it * (uint32_t) (a.colour_seg_start[my_colour] - a.colour_seg_start[my_colour - 1]);
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
             do {
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
               if ((int32_t) (v - target) >= 0 || *(volatile int *) a.err) break;
-              __nanosleep(64);
+              __nanosleep(20);
               if (global_ns() - t0 > 20ull * 1000 * 1000 * 1000) { atomicCAS(a.err, 0, BSB_DEVERR_PEER_TIMEOUT); break; }
             } while (true);
           }
@@ -341,15 +355,21 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
             }
           }
         double pscale = (deg + deg_more) ? a.gamma / (deg + deg_more) * 2 : 0.0;
-        for (int turn = 0; turn < S; turn++) {
-          int cp = cp_more, cn = cn_more, dg = deg + deg_more;
+        int cp_fix = cp_more, cn_fix = cn_more;   // neighbours in other parents: fixed during this class's scan
 #pragma unroll
-          for (int ee = 0; ee < kNbReg; ee++) {
-            const int live = __shfl_sync(0xffffffffu, zfinal, src[ee]);
-            const int zv = src[ee] != lane ? live : zu[ee];
-            cp += zv == zk;
-            cn += zv == zn;
-          }
+        for (int ee = 0; ee < kNbReg; ee++) {
+          cp_fix += zu[ee] == zk;   // -1 (no such neighbour, or one of the own parent) matches no label
+          cn_fix += zu[ee] == zn;
+        }
+        for (int turn = 0; turn < S; turn++) {
+          int cp = cp_fix, cn = cn_fix, dg = deg + deg_more;
+#pragma unroll
+          for (int k = 0; k < kNbReg; k++)
+            if (k < nsp_max) {   // warp-uniform
+              const int live = __shfl_sync(0xffffffffu, zfinal, sps[k]);
+              cp += (k < nsp) & (live == zk);
+              cn += (k < nsp) & (live == zn);
+            }
           if (active && r == turn) {
             if (more_same_parent)   // more than kNbReg neighbours, some of them in the own parent: read those live
               for (int ee = kNbReg; ee < a.maxdeg; ee++) {
@@ -388,9 +408,12 @@ __global__ void __launch_bounds__(kBlock) k_deconv(const DeconvArgs a) {
       zs[tid] = (uint8_t) (active ? zfinal : 255);
       if (a.fuse && !a.stats_only && base + ppb >= count) {
         // the labels of this segment are final (last pass): let the next colour class go before folding the statistics
-        __threadfence();
+        // (the barrier orders every thread's label stores before thread 0's fence, which is cumulative)
         __syncthreads();
-        if (tid == 0) atomicAdd(a.done + my_colour, 1u);
+        if (tid == 0) {
+          __threadfence();
+          atomicAdd(a.done + my_colour, 1u);
+        }
       } else {
         __syncthreads();
       }
