@@ -150,13 +150,21 @@ int select_device(int device) {
                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
   if (device < 0 || device >= count) return fail(BSB200_ERR_INVALID, "device %d out of range (have %d)", device, count);
   CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail(BSB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  // once per device and process: the architecture check (cudaGetDeviceProperties alone takes milliseconds, a third of
+  // the set-up of a Visium-sized chain) and the pool's release threshold
+  static std::mutex mu;
+  static bool checked[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 64 && checked[device]) return BSB200_OK;
+  int major = 0, minor = 0;
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major < 10) return fail(BSB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
   cudaMemPool_t pool;   // keep freed blocks mapped (chain.hpp: pool_alloc)
   CK(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t keep = ~0ull;
   CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  if (device < 64) checked[device] = true;
   return BSB200_OK;
 }
 
