@@ -615,9 +615,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_z, sizeof(int32_t) * cnt);
     if (pin.e == cudaSuccess) pin.e = cudaMallocHost(&chp->h_snap_w, sizeof(double) * cnt);
   });
-  // Unsharded chains order the spots and build the neighbour lists on the device (setup_kernels.cu) from the CSR
-  // arrays, which therefore go first; BSB200_HOST_SETUP=1 keeps the host version (the one sharded chains use).
-  const bool dev_setup = world == 1 && !std::getenv("BSB200_HOST_SETUP");
+  // The spots are ordered and the neighbour lists built on the device (setup_kernels.cu) from the CSR arrays, which
+  // therefore go first; BSB200_HOST_SETUP=1 keeps the host version (same order, tests/test_gpu_zv_setup.py).
+  const bool dev_setup = !std::getenv("BSB200_HOST_SETUP");
   DeviceOrder dorder;
   std::promise<int> csr_promise;
   std::future<int> csr_ready = csr_promise.get_future();
@@ -650,24 +650,27 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if (a->colour && (a->ncolours < 1 || a->ncolours > 64)) return fail(BSB200_ERR_INVALID, "ncolours = %d out of range", a->ncolours);
   if (dev_setup) {
     CK(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
-    if ((rc = dorder.prealloc(n))) { csr_ready.wait(); return rc; }
+    if ((rc = dorder.prealloc(n, n_own))) { csr_ready.wait(); return rc; }
     if ((rc = csr_ready.get())) return fail(rc, "%s", yup.msg.c_str());
     mark("graph upload");
     bool proper = false;
     if (a->colour) {   // range and properness are checked by the scan
       ncol = a->ncolours;
-      if ((rc = dorder.scan(nullptr, ncol, G, ch->stream, bucket_cnt, &dev_maxdeg, &proper))) return rc;
+      if ((rc = dorder.scan(nullptr, ncol, G, plan.g0, plan.g1, plan.lo, plan.hi, ch->stream, bucket_cnt, &dev_maxdeg, &proper))) return rc;
     }
     if (!proper) {   // none given, or e.g. hex offsets on a filled rectangle: colour the graph ourselves
       rc = colour_graph(a->nbr_ptr, a->nbr_idx, n, colour, &ncol);
       if (rc) return rc;
-      if ((rc = dorder.scan(colour.data(), ncol, G, ch->stream, bucket_cnt, &dev_maxdeg, &proper))) return rc;
+      if ((rc = dorder.scan(colour.data(), ncol, G, plan.g0, plan.g1, plan.lo, plan.hi, ch->stream, bucket_cnt, &dev_maxdeg, &proper))) return rc;
       if (!proper) return fail(BSB200_ERR_NEIGHBORS, "internal error: greedy colouring is not proper");
     }
     mark("colouring");
     ch->ord.ncol = ncol;
-    ch->ord.ngroups = G;
+    ch->ord.ngroups = plan.g1 - plan.g0;
     ch->ord.layout(bucket_cnt, choose_segment(n, ncol, d), kOrderAlign, bucket_start);
+    // own spots into their buckets, ghosts behind them; a sharded chain's halo plan (host) reads the own positions
+    if ((rc = dorder.positions(bucket_cnt, bucket_start, plan.ghosts, ch->ord.npos, world > 1 ? &ch->ord.inv : nullptr, ch->stream)))
+      return rc;
   } else {
     if (a->colour) {
       colour.assign(a->colour, a->colour + n);
@@ -690,7 +693,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   ch->ld = (n_pos + (int64_t) plan.ghosts.size() + 31) / 32 * 32;
   mark("spot order");
   if (world > 1) {
-    rc = make_halo_plan(plan, a->nbr_ptr, a->nbr_idx, colour.data(), ncol, ord.inv, n_pos, ch->halo);
+    rc = make_halo_plan(plan, a->nbr_ptr, a->nbr_idx, colour.empty() ? a->colour : colour.data(), ncol, ord.inv, n_pos, ch->halo);
     if (rc) return rc;
     mark("halo plan");
     rc = ch->comm.init(world, rank, a->comm_id);
@@ -765,10 +768,9 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   if (dev_setup) {
     // original ids, initial labels and neighbour lists in internal order, written by the device from the uploaded graph
     const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;
-    if ((rc = ch->ell.alloc(ell_rows * ldp + kSweepPad)) || (rc = ch->z.alloc(ldp + kSweepPad)) ||
-        (rc = ch->orig.alloc(ldp + kSweepPad)))
-      return rc;
-    if ((rc = dorder.place(bucket_cnt, bucket_start, ch->ld, maxdeg, ch->orig.p, ch->z.p, ch->ell.p, s))) return rc;
+    if ((rc = ch->ell.alloc(ell_rows * ldp + kSweepPad)) || (rc = ch->orig.alloc(ldp + kSweepPad))) return rc;
+    if (!ch->comm.peer() && (rc = ch->z.alloc(ldp + kSweepPad))) return rc;   // peer transport: the labels live in the arena
+    if ((rc = dorder.place(ch->ld, maxdeg, ch->orig.p, ch->z.p, ch->ell.p, s))) return rc;
   } else {
     // neighbour ids in internal order (ELL, -1 padded), initial labels and original ids, filled by host threads
     const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;

@@ -120,20 +120,21 @@ int staged_h2d(int device, const StagedCopy *copies, int ncopies) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Spot order and neighbour lists on the device (unsharded chains)
+// Spot order and neighbour lists on the device (own spots [lo, hi) of a rank, all of them for an unsharded chain)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
 constexpr int kScanBlock = 256;
 
-// per spot: bucket key (shard * ncol + colour), identity value for the sort; per bucket: size; flags: max degree,
-// colour out of range / shared with a neighbour
+// Every spot: largest degree, colour in range and not shared with a neighbour (all ranks of a sharded chain look at the
+// whole graph and so take the same decision).  Own spots [lo, hi): bucket key ((shard - g0) * ncol + colour) and identity
+// value for the sort; per own bucket: size.
 __global__ void __launch_bounds__(kScanBlock) k_graph_scan(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                                                           const int32_t *__restrict__ colour, int64_t n, int ncol, int G,
-                                                           uint32_t *__restrict__ key, int32_t *__restrict__ val,
-                                                           unsigned long long *__restrict__ cnt, int32_t *__restrict__ flags) {
+                                                           const int32_t *__restrict__ colour, int64_t n, int ncol, int G, int g0,
+                                                           int nb, int64_t lo, int64_t hi, uint32_t *__restrict__ key,
+                                                           int32_t *__restrict__ val, unsigned long long *__restrict__ cnt,
+                                                           int32_t *__restrict__ flags) {
   extern __shared__ uint32_t hist[];
-  const int nb = G * ncol;
   for (int b = threadIdx.x; b < nb; b += kScanBlock) hist[b] = 0;
   __syncthreads();
   int maxdeg = 0, bad = 0;
@@ -143,10 +144,11 @@ __global__ void __launch_bounds__(kScanBlock) k_graph_scan(const int64_t *__rest
     maxdeg = max(maxdeg, (int) (p1 - p0));
     if (c < 0 || c >= ncol) { bad |= 2; atomicMin(&flags[2], (int32_t) min(j, (int64_t) 0x7fffffff)); continue; }
     for (int64_t p = p0; p < p1; p++) bad |= colour[idx[p]] == c;
-    const int g = (int) ((j * (int64_t) G) / n);
+    if (j < lo || j >= hi) continue;
+    const int g = (int) ((j * (int64_t) G) / n) - g0;
     const uint32_t b = (uint32_t) (g * ncol + c);
-    key[j] = b;
-    val[j] = (int32_t) j;
+    key[j - lo] = b;
+    val[j - lo] = (int32_t) j;
     atomicAdd(&hist[b], 1u);
   }
   __syncthreads();
@@ -161,23 +163,36 @@ __global__ void __launch_bounds__(kScanBlock) k_graph_scan(const int64_t *__rest
 }
 
 // sorted rank t -> internal position: start of the bucket (aligned, holes between buckets) + rank inside it
-__global__ void __launch_bounds__(kScanBlock) k_place(const uint32_t *__restrict__ key, const int32_t *__restrict__ val, int64_t n,
-                                                      const int64_t *__restrict__ start, const int64_t *__restrict__ ustart,
-                                                      const int32_t *__restrict__ init, int32_t *__restrict__ inv,
-                                                      int32_t *__restrict__ orig, uint8_t *__restrict__ z) {
-  for (int64_t t = (int64_t) blockIdx.x * kScanBlock + threadIdx.x; t < n; t += (int64_t) gridDim.x * kScanBlock) {
+__global__ void __launch_bounds__(kScanBlock) k_positions(const uint32_t *__restrict__ key, const int32_t *__restrict__ val,
+                                                          int64_t n_own, const int64_t *__restrict__ start,
+                                                          const int64_t *__restrict__ ustart, int32_t *__restrict__ inv) {
+  for (int64_t t = (int64_t) blockIdx.x * kScanBlock + threadIdx.x; t < n_own; t += (int64_t) gridDim.x * kScanBlock) {
     const uint32_t b = key[t];
-    const int32_t j = val[t];
-    const int64_t pos = start[b] + (t - ustart[b]);
-    inv[j] = (int32_t) pos;
+    inv[val[t]] = (int32_t) (start[b] + (t - ustart[b]));
+  }
+}
+// ghosts (spots of other ranks read by own spots) follow the own positions, in ascending original id
+__global__ void __launch_bounds__(kScanBlock) k_ghost_positions(const int32_t *__restrict__ ghosts, int64_t nghost, int64_t n_pos,
+                                                                int32_t *__restrict__ inv) {
+  for (int64_t g = (int64_t) blockIdx.x * kScanBlock + threadIdx.x; g < nghost; g += (int64_t) gridDim.x * kScanBlock)
+    inv[ghosts[g]] = (int32_t) (n_pos + g);
+}
+// original id and initial label at every position (own spots, then ghosts)
+__global__ void __launch_bounds__(kScanBlock) k_place(const int32_t *__restrict__ ids, int64_t count, const int32_t *__restrict__ inv,
+                                                      const int32_t *__restrict__ init, int32_t *__restrict__ orig,
+                                                      uint8_t *__restrict__ z) {
+  for (int64_t t = (int64_t) blockIdx.x * kScanBlock + threadIdx.x; t < count; t += (int64_t) gridDim.x * kScanBlock) {
+    const int32_t j = ids[t];
+    const int64_t pos = inv[j];
     orig[pos] = j;
     z[pos] = (uint8_t) (init[j] - 1);
   }
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_ell(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int64_t n,
-                                                    const int32_t *__restrict__ inv, int32_t *__restrict__ ell, int64_t ld) {
-  for (int64_t j = (int64_t) blockIdx.x * kScanBlock + threadIdx.x; j < n; j += (int64_t) gridDim.x * kScanBlock) {
+__global__ void __launch_bounds__(kScanBlock) k_ell(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int64_t lo,
+                                                    int64_t hi, const int32_t *__restrict__ inv, int32_t *__restrict__ ell,
+                                                    int64_t ld) {
+  for (int64_t j = lo + (int64_t) blockIdx.x * kScanBlock + threadIdx.x; j < hi; j += (int64_t) gridDim.x * kScanBlock) {
     const int64_t pos = inv[j];
     int e = 0;
     for (int64_t p = ptr[j]; p < ptr[j + 1]; p++, e++) ell[(size_t) e * ld + pos] = inv[idx[p]];
@@ -203,26 +218,27 @@ int DeviceOrder::upload(const int64_t *h_ptr, const int32_t *h_idx, const int32_
   return staged_h2d(device, cp, h_colour ? 4 : 3);
 }
 
-int DeviceOrder::prealloc(int64_t n_) {   // the sort's buffers: allocated by the caller's thread while upload() copies
+int DeviceOrder::prealloc(int64_t n_, int64_t n_own_) {   // the sort's buffers: allocated by the caller's thread while upload() copies
   int rc;
-  if ((rc = key.alloc((size_t) n_)) || (rc = val.alloc((size_t) n_)) || (rc = key2.alloc((size_t) n_)) ||
-      (rc = val2.alloc((size_t) n_)) || (rc = inv.alloc((size_t) n_)) || (rc = flags.alloc(3)))
+  const size_t m = (size_t) std::max<int64_t>(n_own_, 1);
+  if ((rc = key.alloc(m)) || (rc = val.alloc(m)) || (rc = key2.alloc(m)) || (rc = val2.alloc(m)) ||
+      (rc = inv.alloc((size_t) n_)) || (rc = flags.alloc(3)))
     return rc;
   return BSB200_OK;
 }
 
-int DeviceOrder::scan(const int32_t *h_colour_new, int ncol_, int G_, cudaStream_t s, std::vector<int64_t> &cnt, int *maxdeg,
-                      bool *proper) {
-  ncol = ncol_; G = G_;
-  const int nb = G * ncol;
+int DeviceOrder::scan(const int32_t *h_colour_new, int ncol_, int G_, int g0_, int g1_, int64_t lo_, int64_t hi_, cudaStream_t s,
+                      std::vector<int64_t> &cnt, int *maxdeg, bool *proper) {
+  ncol = ncol_; G = G_; g0 = g0_; g1 = g1_; lo = lo_; hi = hi_;
+  const int nb = (g1 - g0) * ncol;
   int rc;
   if ((rc = dcnt.alloc((size_t) nb))) return rc;
   if (h_colour_new) CK(cudaMemcpyAsync(colour.p, h_colour_new, sizeof(int32_t) * (size_t) n, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(dcnt.p, 0, sizeof(unsigned long long) * nb, s));
   const int32_t f0[3] = {0, 0, 0x7fffffff};   // max degree, colouring faults, first spot with a colour out of range
   CK(cudaMemcpyAsync(flags.p, f0, sizeof(f0), cudaMemcpyHostToDevice, s));
-  k_graph_scan<<<grid_for(n), kScanBlock, sizeof(uint32_t) * nb, s>>>(ptr.p, idx.p, colour.p, n, ncol, G, key.p, val.p, dcnt.p,
-                                                                      flags.p);
+  k_graph_scan<<<grid_for(n), kScanBlock, sizeof(uint32_t) * nb, s>>>(ptr.p, idx.p, colour.p, n, ncol, G, g0, nb, lo, hi, key.p, val.p,
+                                                                      dcnt.p, flags.p);
   count_launch();
   CK(cudaGetLastError());
   std::vector<unsigned long long> hc((size_t) nb);
@@ -237,35 +253,59 @@ int DeviceOrder::scan(const int32_t *h_colour_new, int ncol_, int G_, cudaStream
   return BSB200_OK;
 }
 
-int DeviceOrder::place(const std::vector<int64_t> &cnt, const std::vector<int64_t> &start, int64_t ld, int maxdeg, int32_t *d_orig,
-                       uint8_t *d_z, int32_t *d_ell, cudaStream_t s) {
-  const int nb = G * ncol;
+int DeviceOrder::positions(const std::vector<int64_t> &cnt, const std::vector<int64_t> &start, const std::vector<int32_t> &ghost_ids,
+                           int64_t n_pos, std::vector<int32_t> *own_inv, cudaStream_t s) {
+  const int nb = (g1 - g0) * ncol;
+  const int64_t n_own = hi - lo;
   std::vector<int64_t> ustart((size_t) nb + 1, 0);
   for (int b = 0; b < nb; b++) ustart[(size_t) b + 1] = ustart[(size_t) b] + cnt[(size_t) b];
   DevBuf<int64_t> dstart, dustart;
   DevBuf<unsigned char> temp;
   int rc;
-  if ((rc = dstart.alloc((size_t) nb)) || (rc = dustart.alloc((size_t) nb + 1))) return rc;
+  if ((rc = dstart.alloc((size_t) nb)) || (rc = dustart.alloc((size_t) nb + 1)) || (rc = ghosts.alloc(ghost_ids.size()))) return rc;
   CK(cudaMemcpyAsync(dstart.p, start.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(dustart.p, ustart.data(), sizeof(int64_t) * (nb + 1), cudaMemcpyHostToDevice, s));
+  if (!ghost_ids.empty())
+    CK(cudaMemcpyAsync(ghosts.p, ghost_ids.data(), sizeof(int32_t) * ghost_ids.size(), cudaMemcpyHostToDevice, s));
   int bits = 1;
   while ((1 << bits) < nb) bits++;
   size_t temp_bytes = 0;
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, key.p, key2.p, val.p, val2.p, (int64_t) n, 0, bits, s));
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, key.p, key2.p, val.p, val2.p, (int64_t) n_own, 0, bits, s));
   if ((rc = temp.alloc(temp_bytes))) return rc;
-  CK(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, key.p, key2.p, val.p, val2.p, (int64_t) n, 0, bits, s));   // stable
+  CK(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, key.p, key2.p, val.p, val2.p, (int64_t) n_own, 0, bits, s));   // stable
   count_launch();
+  k_positions<<<grid_for(n_own), kScanBlock, 0, s>>>(key2.p, val2.p, n_own, dstart.p, dustart.p, inv.p);
+  count_launch();
+  if (!ghost_ids.empty()) {
+    k_ghost_positions<<<grid_for((int64_t) ghost_ids.size()), kScanBlock, 0, s>>>(ghosts.p, (int64_t) ghost_ids.size(), n_pos, inv.p);
+    count_launch();
+  }
+  CK(cudaGetLastError());
+  if (own_inv) {   // the halo plan of a sharded chain (host) addresses the own spots by position
+    own_inv->resize((size_t) n_own);
+    CK(cudaMemcpyAsync(own_inv->data(), inv.p + lo, sizeof(int32_t) * (size_t) n_own, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));   // the temporaries go out of scope
+  return BSB200_OK;
+}
+
+int DeviceOrder::place(int64_t ld, int maxdeg, int32_t *d_orig, uint8_t *d_z, int32_t *d_ell, cudaStream_t s) {
+  const int64_t n_own = hi - lo;
   const size_t ell_rows = (size_t) std::max(maxdeg, 1);
   CK(cudaMemsetAsync(d_orig, 0xff, sizeof(int32_t) * ((size_t) ld + kSweepPad), s));                 // -1: holes, padding
   CK(cudaMemsetAsync(d_ell, 0xff, sizeof(int32_t) * (ell_rows * (size_t) ld + kSweepPad), s));
   CK(cudaMemsetAsync(d_z, 0, (size_t) ld, s));
   CK(cudaMemsetAsync(d_z + ld, 255, (size_t) kSweepPad, s));   // the label no cluster has (padding neighbour entries)
-  k_place<<<grid_for(n), kScanBlock, 0, s>>>(key2.p, val2.p, n, dstart.p, dustart.p, init.p, inv.p, d_orig, d_z);
+  k_place<<<grid_for(n_own), kScanBlock, 0, s>>>(val2.p, n_own, inv.p, init.p, d_orig, d_z);
   count_launch();
-  k_ell<<<grid_for(n), kScanBlock, 0, s>>>(ptr.p, idx.p, n, inv.p, d_ell, ld);
+  if (ghosts.count) {
+    k_place<<<grid_for((int64_t) ghosts.count), kScanBlock, 0, s>>>(ghosts.p, (int64_t) ghosts.count, inv.p, init.p, d_orig, d_z);
+    count_launch();
+  }
+  k_ell<<<grid_for(n_own), kScanBlock, 0, s>>>(ptr.p, idx.p, lo, hi, inv.p, d_ell, ld);
   count_launch();
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(s));   // the temporaries go out of scope
+  CK(cudaStreamSynchronize(s));
   return BSB200_OK;
 }
 

@@ -1,8 +1,9 @@
-"""Set-up of an unsharded chain on the device (csrc/setup_kernels.cu) against the host set-up (csrc/chain.cu).
+"""Set-up of a chain on the device (csrc/setup_kernels.cu) against the host set-up (csrc/chain.cu).
 
 The device path uploads the caller's CSR graph through the staged copies, checks the colouring, orders the spots by
 (virtual shard, colour, original id) with a stable radix sort and writes the neighbour lists in internal order; the host
-path (BSB200_HOST_SETUP=1, the one sharded chains use) does the same with host threads.  Both must give the same
+path (BSB200_HOST_SETUP=1) does the same with host threads.  Sharded chains take the device path too (own spots and
+ghosts of every rank): tests/mgpu_check.py compares them bit for bit with the unsharded chain.  Both must give the same
 internal order, hence bit-identical chains: labels, parameters, weights and plogLik are compared with array_equal.
 The chains themselves are checked against the CPU oracle elsewhere (test_gpu_parity.py, test_gpu_zy_clusters.py).
 """
