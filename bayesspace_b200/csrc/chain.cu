@@ -564,6 +564,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     std::fprintf(stderr, "[bsb200 setup r%d] %-22s %8.1f ms\n", a->world > 1 ? a->rank : 0, what, t - t_last);
     t_last = t;
   };
+  set_host_share(a && a->world > 1 ? a->world : 1);
   int rc = validate(a);
   if (rc) return rc;
   rc = select_device(a->device);

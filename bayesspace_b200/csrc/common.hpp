@@ -40,6 +40,7 @@ bool colouring_is_proper(const int64_t *ptr, const int32_t *idx, int64_t n, cons
 // Host threads for the O(n) set-up loops (validation, ordering, ELL staging): chunks [lo, hi) of [0, n) run on up to
 // BSB200_HOST_THREADS (default: min(hardware threads, 16)) threads; small n runs inline.  fn must be thread-safe.
 int host_threads();
+void set_host_share(int ranks_on_this_host);   // sharded chains: host threads per rank = host_threads() / ranks
 template <typename F>
 inline void parallel_for(int64_t n, F fn, int64_t min_chunk = 1 << 18) {
   int nt = host_threads();
@@ -51,8 +52,9 @@ inline void parallel_for(int64_t n, F fn, int64_t min_chunk = 1 << 18) {
   fn((int64_t) 0, n / nt, 0);
   for (auto &x : th) x.join();
 }
-inline int parallel_chunks(int64_t n, int64_t min_chunk = 1 << 18) {   // number of chunks parallel_for will use
-  int nt = host_threads();
+int host_threads_max();
+inline int parallel_chunks(int64_t n, int64_t min_chunk = 1 << 18) {   // upper bound of the chunks parallel_for will use
+  int nt = host_threads_max();
   if ((int64_t) nt > n / min_chunk) nt = (int) (n / min_chunk);
   return nt < 1 ? 1 : nt;
 }

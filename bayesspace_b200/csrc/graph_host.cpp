@@ -9,6 +9,8 @@
 //   convert_neighbors2mtx    src/cluster.cpp:147-159
 #include "common.hpp"
 
+#include <atomic>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cmath>
@@ -283,13 +285,22 @@ int colour_graph(const int64_t *ptr, const int32_t *idx, int64_t n, std::vector<
 }
 
 // true when no directed edge joins two spots of one colour (self loops excepted)
-int host_threads() {
+static std::atomic<int> g_host_share{1};
+void set_host_share(int ranks_on_this_host) { g_host_share.store(ranks_on_this_host < 1 ? 1 : ranks_on_this_host); }
+int host_threads_max() {
   static const int nt = []() {
     int v = (int) std::thread::hardware_concurrency();
     if (const char *e = std::getenv("BSB200_HOST_THREADS")) v = std::atoi(e);
     return v < 1 ? 1 : (v > 16 ? 16 : v);
   }();
   return nt;
+}
+int host_threads() {
+  const int nt = host_threads_max();
+  // The ranks of a sharded chain share the host's cores, but their O(n) loops rarely coincide: dividing the threads
+  // by the rank count made the set-up at 8 ranks slower (halo plan 15 -> 40 ms), so a rank keeps at least half of them.
+  const int share = g_host_share.load(std::memory_order_relaxed);
+  return share > 1 ? std::max(nt / 2, nt / share) : nt;
 }
 
 bool colouring_is_proper(const int64_t *ptr, const int32_t *idx, int64_t n, const int32_t *colour) {

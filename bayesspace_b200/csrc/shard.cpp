@@ -23,9 +23,14 @@ int make_shard_plan(int64_t n, const int64_t *ptr, const int32_t *idx, int group
   plan.hi = plan.group_lo[(size_t) plan.g1];
   plan.ghosts.clear();
   if (world > 1) {
-    for (int64_t j = plan.lo; j < plan.hi; j++)
-      for (int64_t e = ptr[j]; e < ptr[j + 1]; e++)
-        if (idx[e] < plan.lo || idx[e] >= plan.hi) plan.ghosts.push_back(idx[e]);
+    const int nchunk = parallel_chunks(plan.hi - plan.lo);
+    std::vector<std::vector<int32_t>> part((size_t) nchunk);
+    parallel_for(plan.hi - plan.lo, [&](int64_t a, int64_t b, int t) {
+      for (int64_t j = plan.lo + a; j < plan.lo + b; j++)
+        for (int64_t e = ptr[j]; e < ptr[j + 1]; e++)
+          if (idx[e] < plan.lo || idx[e] >= plan.hi) part[(size_t) t].push_back(idx[e]);
+    });
+    for (auto &v : part) plan.ghosts.insert(plan.ghosts.end(), v.begin(), v.end());
     std::sort(plan.ghosts.begin(), plan.ghosts.end());
     plan.ghosts.erase(std::unique(plan.ghosts.begin(), plan.ghosts.end()), plan.ghosts.end());
   }
