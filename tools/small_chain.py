@@ -1,3 +1,5 @@
+"""Development driver: wall clock, set-up and device time of repeated bsb200_cluster() calls at Visium size (C2 lattice);
+BSB200_TIMING=1 adds the library's marks."""
 import sys, time; sys.path.insert(0,'.')
 import numpy as np
 import bayesspace_b200 as B, bench
