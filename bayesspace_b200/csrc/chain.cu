@@ -596,7 +596,11 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   const int64_t n_own = ch->n_own;
   // The PCs are the bulk of the input (1.2 GB at 10M spots): their upload runs on a second host thread while this one
   // colours, orders and stages the graph.  Own rows of Y (R's column-major n x d): one strided copy.
+  // (everything the upload thread touches is declared before the thread's owner, i.e. outlives its join on any return)
   DevBuf<double> Yraw;
+  DeviceOrder dorder;
+  std::promise<int> csr_promise;
+  std::future<int> csr_ready = csr_promise.get_future();
   struct Uploader {
     std::thread th;
     int rc = BSB200_OK;
@@ -619,9 +623,6 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
   // The spots are ordered and the neighbour lists built on the device (setup_kernels.cu) from the CSR arrays, which
   // therefore go first; BSB200_HOST_SETUP=1 keeps the host version (same order, tests/test_gpu_zv_setup.py).
   const bool dev_setup = !std::getenv("BSB200_HOST_SETUP");
-  DeviceOrder dorder;
-  std::promise<int> csr_promise;
-  std::future<int> csr_ready = csr_promise.get_future();
   yup.th = std::thread([&, device = a->device]() {
     cudaError_t e = cudaSetDevice(device);
     if (dev_setup) {
@@ -772,6 +773,7 @@ int chain_create_impl(const bsb200_cluster_args *a, bsb200_chain **out) {
     if ((rc = ch->ell.alloc(ell_rows * ldp + kSweepPad)) || (rc = ch->orig.alloc(ldp + kSweepPad))) return rc;
     if (!ch->comm.peer() && (rc = ch->z.alloc(ldp + kSweepPad))) return rc;   // peer transport: the labels live in the arena
     if ((rc = dorder.place(ch->ld, maxdeg, ch->orig.p, ch->z.p, ch->ell.p, s))) return rc;
+    dorder.release();   // 0.6 GB of graph copies and sort buffers at 10M spots go back to the pool before Y is laid out
   } else {
     // neighbour ids in internal order (ELL, -1 padded), initial labels and original ids, filled by host threads
     const size_t ell_rows = (size_t) std::max(maxdeg, 1), ldp = (size_t) ch->ld;
@@ -1112,6 +1114,7 @@ int bsb200_release_memory(int32_t device) {
   int32_t *z = nullptr;
   double *w = nullptr;
   if (g_pinned.take(device, 0, &z, &w)) { cudaFreeHost(z); cudaFreeHost(w); }
+  staged_release();
   return BSB200_OK;
 }
 

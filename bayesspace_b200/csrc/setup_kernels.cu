@@ -119,6 +119,11 @@ int staged_h2d(int device, const StagedCopy *copies, int ncopies) {
   return BSB200_OK;
 }
 
+void staged_release() {
+  std::lock_guard<std::mutex> lock(g_pool.mu);
+  if (g_pool.ready) g_pool.release();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Spot order and neighbour lists on the device (own spots [lo, hi) of a rank, all of them for an unsharded chain)
 // ------------------------------------------------------------------------------------------------
@@ -287,6 +292,11 @@ int DeviceOrder::positions(const std::vector<int64_t> &cnt, const std::vector<in
   }
   CK(cudaStreamSynchronize(s));   // the temporaries go out of scope
   return BSB200_OK;
+}
+
+void DeviceOrder::release() {
+  ptr.release(); idx.release(); init.release(); colour.release(); val.release(); val2.release(); inv.release();
+  ghosts.release(); key.release(); key2.release(); dcnt.release(); flags.release();
 }
 
 int DeviceOrder::place(int64_t ld, int maxdeg, int32_t *d_orig, uint8_t *d_z, int32_t *d_ell, cudaStream_t s) {

@@ -19,6 +19,7 @@ struct StagedCopy {
   size_t bytes;
 };
 int staged_h2d(int device, const StagedCopy *copies, int ncopies);
+void staged_release();   // frees the page-locked staging buffers (bsb200_release_memory)
 
 // Internal spot order of a chain -- of the spots [lo, hi) = virtual shards [g0, g1) a rank owns -- computed on the
 // device from the caller's CSR graph: upload() copies the graph; scan() returns the sizes of the own (shard, colour)
@@ -41,6 +42,7 @@ struct DeviceOrder {
   int positions(const std::vector<int64_t> &cnt, const std::vector<int64_t> &start, const std::vector<int32_t> &ghost_ids, int64_t n_pos,
                 std::vector<int32_t> *own_inv, cudaStream_t s);
   int place(int64_t ld, int maxdeg, int32_t *d_orig, uint8_t *d_z, int32_t *d_ell, cudaStream_t s);
+  void release();   // every device buffer (the upload thread must have delivered the graph)
 };
 
 }   // namespace bsb
