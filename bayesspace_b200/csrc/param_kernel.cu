@@ -131,18 +131,21 @@ __device__ __noinline__ void warp_revchol_reg(double *U, int lane, int *ok) {
   __syncwarp();
 }
 
-// T = U^-1 (upper), row by row from the bottom; U and T in shared memory (may not alias).
+// T = U^-1 (upper), from the bottom row up; U and T in shared memory (may not alias).  Column `lane` of T lives in
+// registers; as soon as t[i] is final it is taken out of the partial sums of all rows above (independent FMAs) instead
+// of every row summing its dependent chain when its turn comes: d dependent steps instead of d (d - 1) / 2.
 template <int D>
 __device__ __noinline__ void warp_inv_upper_reg(const double *U, double *T, int lane) {
-  double t[D];   // column `lane` of T; t[k] = 0 for k > lane, so the sums below need no predicate
+  double t[D], s[D];   // t[k] = 0 for k > lane
   if (lane < D) T[lane * D + lane] = 1.0 / U[lane * D + lane];   // reciprocal diagonals, read back as broadcasts
+#pragma unroll
+  for (int i = 0; i < D; i++) s[i] = lane == i ? 1.0 : 0.0;
   __syncwarp();
 #pragma unroll
   for (int i = D - 1; i >= 0; i--) {
-    double s = lane == i ? 1.0 : 0.0;
+    t[i] = lane >= i ? s[i] * T[i * D + i] : 0.0;
 #pragma unroll
-    for (int k = i + 1; k < D; k++) s = fma(-U[k * D + i], t[k], s);   // broadcast loads of U[i,k]
-    t[i] = lane >= i ? s * T[i * D + i] : 0.0;
+    for (int i2 = 0; i2 < i; i2++) s[i2] = fma(-U[i * D + i2], t[i], s[i2]);   // broadcast loads of U[i2, i]
   }
   __syncwarp();
 #pragma unroll
