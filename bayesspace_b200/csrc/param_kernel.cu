@@ -179,22 +179,36 @@ __global__ void __launch_bounds__(D > 0 ? 512 : 256) k_param(ParamArgs a, int st
 
   // ---- (0) deterministic two-level reduction of the segment partials ---------------------------
   double *const gsum = a.gsum + (a.gepoch ? (size_t) (*a.gepoch & 1u) * a.gsum_stride : (size_t) 0);
-  for (int idx = tid; !a.gsum_ready && idx < E * a.ngroups; idx += nt) {
-    const int e = idx % E, g = idx / E;
-    // slots of a shard folded in slot order (fixed association); loads issued 8 at a time ahead of the adds
-    const int s0 = a.group_start[g], s1 = a.group_start[g + 1];
-    const double *pp = a.partials + e;
-    double s = 0.0;
-    int slot = s0;
-    for (; slot + 8 <= s1; slot += 8) {
-      double v[8];
+  if (!a.gsum_ready) {
+    // Level 1 (chains with one virtual shard fold here; the others in k_reduce_groups): the slots of a shard are summed in
+    // slot order, by 1, 2 or 4 adjacent lanes per sum when threads are to spare -- each lane a contiguous part of the
+    // slots, the parts added in order -- so that a 250-slot fold (deconvolution at 30k subspots) is 8 rounds of eight
+    // loads instead of 32.  The association depends on (E, slots) only: deterministic, and no other GPU count shares it.
+    const int total = E * a.ngroups;
+    int ways = 1;
+    while (ways < 4 && total * ways * 2 <= nt) ways *= 2;
+    for (int base = 0; base < total * ways; base += nt) {   // uniform trip count: the shuffles below are warp-wide
+      const int idx = base + tid, pair = idx / ways, part = idx - pair * ways;
+      const bool valid = pair < total;
+      const int e = valid ? pair % E : 0, g = valid ? pair / E : 0;
+      const int s0 = a.group_start[g], s1 = valid ? a.group_start[g + 1] : s0;
+      const int chunk = (s1 - s0 + ways - 1) / ways;
+      int slot = min(s1, s0 + part * chunk);
+      const int end = min(s1, slot + chunk);
+      const double *pp = a.partials + e;
+      double s = 0.0;
+      for (; slot + 8 <= end; slot += 8) {   // loads issued 8 at a time ahead of the adds
+        double v[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = __ldcg(pp + (size_t) (slot + u) * E);
+        for (int u = 0; u < 8; u++) v[u] = __ldcg(pp + (size_t) (slot + u) * E);
 #pragma unroll
-      for (int u = 0; u < 8; u++) s += v[u];
+        for (int u = 0; u < 8; u++) s += v[u];
+      }
+      for (; slot < end; slot++) s += __ldcg(pp + (size_t) slot * E);
+      const double p1 = __shfl_down_sync(0xffffffffu, s, 1), p2 = __shfl_down_sync(0xffffffffu, s, 2),
+                   p3 = __shfl_down_sync(0xffffffffu, s, 3);
+      if (valid && part == 0) gsum[(size_t) g * E + e] = ways == 1 ? s : (ways == 2 ? s + p1 : ((s + p1) + p2) + p3);
     }
-    for (; slot < s1; slot++) s += __ldcg(pp + (size_t) slot * E);
-    gsum[(size_t) g * E + e] = s;
   }
   __syncthreads();
   for (int e = tid; e < E; e += nt) {
