@@ -364,6 +364,7 @@ struct bsb200_chain {
       t = t2;
     };
     if (stream) cudaStreamSynchronize(stream);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);   // a snapshot copy of an aborted run may still be in flight
     mark("sync");
     if (graph_iter) cudaGraphExecDestroy(graph_iter);     // graphs first: NCCL waits for the graphs that captured it
     if (graph_batch) cudaGraphExecDestroy(graph_batch);
