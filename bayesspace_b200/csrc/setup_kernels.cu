@@ -130,6 +130,7 @@ void staged_release() {
 namespace {
 
 constexpr int kScanBlock = 256;
+constexpr int kMaxSmemBuckets = 8192;   // 32 KB of block-local histogram
 
 // Every spot: largest degree, colour in range and not shared with a neighbour (all ranks of a sharded chain look at the
 // whole graph and so take the same decision).  Own spots [lo, hi): bucket key ((shard - g0) * ncol + colour) and identity
@@ -140,8 +141,11 @@ __global__ void __launch_bounds__(kScanBlock) k_graph_scan(const int64_t *__rest
                                                            int32_t *__restrict__ val, unsigned long long *__restrict__ cnt,
                                                            int32_t *__restrict__ flags) {
   extern __shared__ uint32_t hist[];
-  for (int b = threadIdx.x; b < nb; b += kScanBlock) hist[b] = 0;
-  __syncthreads();
+  const bool in_smem = nb <= kMaxSmemBuckets;   // more buckets than that (thousands of shards x colours): global atomics
+  if (in_smem) {
+    for (int b = threadIdx.x; b < nb; b += kScanBlock) hist[b] = 0;
+    __syncthreads();
+  }
   int maxdeg = 0, bad = 0;
   for (int64_t j = (int64_t) blockIdx.x * kScanBlock + threadIdx.x; j < n; j += (int64_t) gridDim.x * kScanBlock) {
     const int32_t c = colour[j];
@@ -154,11 +158,14 @@ __global__ void __launch_bounds__(kScanBlock) k_graph_scan(const int64_t *__rest
     const uint32_t b = (uint32_t) (g * ncol + c);
     key[j - lo] = b;
     val[j - lo] = (int32_t) j;
-    atomicAdd(&hist[b], 1u);
+    if (in_smem) atomicAdd(&hist[b], 1u);
+    else atomicAdd(&cnt[b], 1ull);
   }
-  __syncthreads();
-  for (int b = threadIdx.x; b < nb; b += kScanBlock)
-    if (hist[b]) atomicAdd(&cnt[b], (unsigned long long) hist[b]);
+  if (in_smem) {
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += kScanBlock)
+      if (hist[b]) atomicAdd(&cnt[b], (unsigned long long) hist[b]);
+  }
   maxdeg = __reduce_max_sync(0xffffffffu, maxdeg);
   bad = __reduce_or_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0) {
@@ -242,7 +249,7 @@ int DeviceOrder::scan(const int32_t *h_colour_new, int ncol_, int G_, int g0_, i
   CK(cudaMemsetAsync(dcnt.p, 0, sizeof(unsigned long long) * nb, s));
   const int32_t f0[3] = {0, 0, 0x7fffffff};   // max degree, colouring faults, first spot with a colour out of range
   CK(cudaMemcpyAsync(flags.p, f0, sizeof(f0), cudaMemcpyHostToDevice, s));
-  k_graph_scan<<<grid_for(n), kScanBlock, sizeof(uint32_t) * nb, s>>>(ptr.p, idx.p, colour.p, n, ncol, G, g0, nb, lo, hi, key.p, val.p,
+  k_graph_scan<<<grid_for(n), kScanBlock, nb <= kMaxSmemBuckets ? sizeof(uint32_t) * nb : 0, s>>>(ptr.p, idx.p, colour.p, n, ncol, G, g0, nb, lo, hi, key.p, val.p,
                                                                       dcnt.p, flags.p);
   count_launch();
   CK(cudaGetLastError());
